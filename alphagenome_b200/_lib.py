@@ -1,0 +1,125 @@
+"""ctypes binding of libagb200.so (the C ABI in include/agb200.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing, or the device is not an
+sm_100 part, every op raises.  torch is used only for device memory, streams and distributed plumbing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libagb200.so"
+
+
+class AgEpiOut(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("bstride", C.c_int64),
+        ("shift_bstride", C.c_int64),
+        ("ld", C.c_int32),
+        ("act", C.c_int32),
+        ("dtype", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class AgGemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p),
+        ("a_bstride", C.c_int64),
+        ("a_ld", C.c_int32),
+        ("a_rows", C.c_int32),
+        ("a_row0", C.c_int32),
+        ("w_batched", C.c_int32),
+        ("W", C.c_void_p),
+        ("w_zstride", C.c_int64),
+        ("w_ld", C.c_int32),
+        ("batch", C.c_int32),
+        ("M", C.c_int32),
+        ("N", C.c_int32),
+        ("K", C.c_int32),
+        ("taps", C.c_int32),
+        ("pre_scale", C.c_void_p),
+        ("pre_shift", C.c_void_p),
+        ("relu", C.c_int32),
+        ("res_ch", C.c_int32),
+        ("res", C.c_void_p),
+        ("res_bstride", C.c_int64),
+        ("res_ld", C.c_int32),
+        ("res_shift", C.c_int32),
+        ("post_scale", C.c_void_p),
+        ("out", C.c_void_p),
+        ("out_bstride", C.c_int64),
+        ("out_ld", C.c_int32),
+        ("pool_ld", C.c_int32),
+        ("pool", C.c_void_p),
+        ("pool_bstride", C.c_int64),
+        ("actA", AgEpiOut),
+        ("actB", AgEpiOut),
+        ("actP", AgEpiOut),
+    ]
+
+
+ACT_NONE, ACT_GELU1702, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
+
+# every symbol include/agb200.h declares; tests check the built library exports all of them
+EXPORTED = [
+    "ag_version",
+    "ag_last_error",
+    "ag_launch_count",
+    "ag_check_device",
+    "ag_watchdog_status",
+    "ag_gemm_fwd",
+]
+
+_lib = None
+
+
+class AgbError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libagb200.so (building is `python -m alphagenome_b200.csrc.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise AgbError(
+            f"{LIB_PATH} is missing: build it with `python -m alphagenome_b200.csrc.build` "
+            "(there is no CPU/PyTorch fallback for the trunk kernels)"
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    lib.ag_version.restype = C.c_int
+    lib.ag_last_error.restype = C.c_char_p
+    lib.ag_launch_count.restype = C.c_uint64
+    lib.ag_check_device.argtypes = [C.c_int]
+    lib.ag_check_device.restype = C.c_int
+    lib.ag_watchdog_status.argtypes = [C.c_int, C.POINTER(C.c_uint32 * 4)]
+    lib.ag_watchdog_status.restype = C.c_int
+    lib.ag_gemm_fwd.argtypes = [C.POINTER(AgGemmArgs), C.c_int, C.c_void_p]
+    lib.ag_gemm_fwd.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().ag_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise AgbError(last_error())
+
+
+def launch_count() -> int:
+    return int(load().ag_launch_count())
+
+
+def watchdog_status(device: int = 0):
+    out = (C.c_uint32 * 4)()
+    load().ag_watchdog_status(device, C.byref(out))
+    return tuple(int(x) for x in out)

@@ -1,0 +1,138 @@
+// C-ABI surface of libagb200.so (declared in include/agb200.h) and the small host runtime behind it:
+// thread-local error text, launch accounting, per-device watchdog word, TMA descriptor encoding.
+#include <atomic>
+#include <mutex>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "kernels.h"
+
+namespace agb {
+
+static thread_local char tl_error[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::mutex g_mu;
+static unsigned int* g_err_host[64] = {nullptr};
+static unsigned int* g_err_dev[64] = {nullptr};
+static int g_sm_count[64] = {0};
+static int g_cc[64] = {0};
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+static int ensure_device(int device) {
+  if (device < 0 || device >= 64) return set_error("bad device index %d", device);
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) return set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+  if (cur != device) {
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  }
+  if (g_sm_count[device] == 0) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_sm_count[device] == 0) {
+      cudaDeviceProp prop;
+      e = cudaGetDeviceProperties(&prop, device);
+      if (e != cudaSuccess) return set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+      g_cc[device] = prop.major * 10 + prop.minor;
+      void* h = nullptr;
+      e = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+      if (e != cudaSuccess) return set_error("cudaHostAlloc(watchdog): %s", cudaGetErrorString(e));
+      memset(h, 0, 64);
+      void* d = nullptr;
+      e = cudaHostGetDevicePointer(&d, h, 0);
+      if (e != cudaSuccess) return set_error("cudaHostGetDevicePointer: %s", cudaGetErrorString(e));
+      g_err_host[device] = static_cast<unsigned int*>(h);
+      g_err_dev[device] = static_cast<unsigned int*>(d);
+      g_sm_count[device] = prop.multiProcessorCount;
+    }
+  }
+  if (g_cc[device] != 100) return set_error("device %d is sm_%d; libagb200 is built for sm_100a (B200) only", device, g_cc[device]);
+  return 0;
+}
+
+unsigned int* device_error_word(int device) { return g_err_dev[device]; }
+int sm_count(int device) { return g_sm_count[device]; }
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  if (!g_encode) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+      if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
+                        bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return set_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu] box=[%u,%u,%u] base=%p",
+                     (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                     (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)strides_bytes[0],
+                     (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), box[0], rank > 1 ? box[1] : 0,
+                     rank > 2 ? box[2] : 0, base);
+  }
+  return 0;
+}
+
+}  // namespace agb
+
+using namespace agb;
+
+extern "C" {
+
+int ag_version(void) { return AGB200_VERSION; }
+const char* ag_last_error(void) { return tl_error; }
+uint64_t ag_launch_count(void) { return g_launches.load(); }
+
+int ag_check_device(int device) { return ensure_device(device); }
+
+int ag_watchdog_status(int device, uint32_t out[4]) {
+  if (device < 0 || device >= 64 || !g_err_host[device]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    return 0;
+  }
+  for (int i = 0; i < 4; ++i) out[i] = g_err_host[device][i];
+  return out[0] != 0;
+}
+
+int ag_gemm_fwd(const AgGemmArgs* args, int device, void* stream) {
+  if (!args) return set_error("ag_gemm_fwd: null args");
+  if (int rc = ensure_device(device)) return rc;
+  return launch_gemm(*args, device, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

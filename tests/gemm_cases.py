@@ -1,0 +1,138 @@
+"""Shared GEMM/conv parity cases: the CUDA kernel (through the C ABI) against a plain fp32 torch restatement
+of agb200.h's ag_gemm_fwd formula on the same bf16-rounded operands."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from alphagenome_b200 import ops
+
+
+def act_ref(x, mode):
+    if mode == ops.ACT_GELU1702:
+        return torch.sigmoid(1.702 * x) * x
+    if mode == ops.ACT_GELU_ERF:
+        return torch.nn.functional.gelu(x)
+    if mode == ops.ACT_RELU:
+        return torch.relu(x)
+    return x
+
+
+def ref_acc(A, W, M, a_row0, w_batched):
+    """fp64 accumulate of sum_t sum_k A[b, r + t - taps/2 (+row0), k] W[z, n, k]; zero outside the buffer."""
+    Af, Wf = A.double(), W.double()
+    b, rows, K = A.shape
+    N = W.shape[1]
+    taps = 1 if w_batched else W.shape[0]
+    acc = torch.zeros(b, M, N, dtype=torch.float64, device=A.device)
+    r = torch.arange(M, device=A.device)
+    for t in range(taps):
+        idx = r + a_row0 + t - taps // 2
+        ok = (idx >= 0) & (idx < rows)
+        X = torch.zeros(b, M, K, dtype=torch.float64, device=A.device)
+        X[:, ok] = Af[:, idx[ok]]
+        if w_batched:
+            acc += torch.einsum("bmk,bnk->bmn", X, Wf)
+        else:
+            acc += X @ Wf[t].T
+    return acc
+
+
+def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogue="plain", seed=0, strided=False):
+    """Returns dict(name, ok, max_err, details...). Tolerance: fp32-accumulate of bf16 products, so the only
+    error is summation order -> 2e-3 relative to the output scale is generous and still catches any
+    descriptor/layout bug (those give O(1) errors)."""
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    rows = M + 2 * a_row0
+    if strided:
+        # head-batched layout used by the pair kernels: storage [rows, batch, K], batch stride = K
+        A_store = (torch.randn(rows, batch, K, generator=gen) * 0.5).to(dev).bfloat16()
+        A = A_store.permute(1, 0, 2)
+        W_store = (torch.randn(N, batch, K, generator=gen) * 0.5).to(dev).bfloat16()
+        W = W_store.permute(1, 0, 2)
+    else:
+        A = (torch.randn(batch, rows, K, generator=gen) * 0.5).to(dev).bfloat16()
+        nz = batch if w_batched else taps
+        W = (torch.randn(nz, N, K, generator=gen) / math.sqrt(K * taps)).to(dev).bfloat16()
+    acc = ref_acc(A, W, M, a_row0, w_batched)
+
+    res = {}
+    kw = {}
+    checks = []
+    f32 = dict(dtype=torch.float32, device=dev)
+    if epilogue == "plain":
+        out = torch.full((batch, M, N), float("nan"), **f32)
+        kw["out"] = out
+        checks.append(("out", out, acc))
+    elif epilogue == "full":
+        pre_s = (torch.rand(N, generator=gen) + 0.5).to(dev)
+        pre_t = torch.randn(N, generator=gen).to(dev)
+        res_ch = N - 16 if N > 16 else N
+        resid = torch.randn(batch, (M + 1) // 2, res_ch, generator=gen).to(dev)
+        post = torch.tensor([0.75], **f32)
+        sA = (torch.rand(N, generator=gen) + 0.5).to(dev)
+        tA = torch.randn(batch, N, generator=gen).to(dev)
+        sB = (torch.rand(N, generator=gen) + 0.5).to(dev)
+        tB = torch.randn(N, generator=gen).to(dev)
+        sP = (torch.rand(N, generator=gen) + 0.5).to(dev)
+        tP = torch.randn(N, generator=gen).to(dev)
+        out = torch.full((batch, M, N), float("nan"), **f32)
+        dA = torch.zeros(batch, M, N, dtype=torch.bfloat16, device=dev)
+        dB = torch.full((batch, M, N), float("nan"), **f32)
+        pool = torch.full((batch, M // 2, N), float("nan"), **f32)
+        dP = torch.zeros(batch, M // 2, N, dtype=torch.bfloat16, device=dev)
+        kw.update(pre_scale=pre_s, pre_shift=pre_t, res=resid, res_ch=res_ch, res_shift=1, post_scale=post, out=out,
+                  actA=ops.Act(dA, sA, tA, ops.ACT_GELU1702), actB=ops.Act(dB, sB, tB, ops.ACT_GELU_ERF),
+                  pool=pool, actP=ops.Act(dP, sP, tP, ops.ACT_GELU1702))
+        v = acc * pre_s.double() + pre_t.double()
+        rr = torch.arange(M, device=dev) >> 1
+        v[:, :, :res_ch] += resid.double()[:, rr]
+        v = v * 0.75
+        checks.append(("out", out, v))
+        checks.append(("actA", dA, act_ref(v * sA.double() + tA.double()[:, None], ops.ACT_GELU1702)))
+        checks.append(("actB", dB, act_ref(v * sB.double() + tB.double(), ops.ACT_GELU_ERF)))
+        pv = torch.maximum(v[:, 0::2], v[:, 1::2])
+        checks.append(("pool", pool, pv))
+        checks.append(("actP", dP, act_ref(pv * sP.double() + tP.double(), ops.ACT_GELU1702)))
+    elif epilogue == "relu_bf16":
+        bias = torch.randn(N, generator=gen).to(dev)
+        dA = torch.zeros(batch, M, N, dtype=torch.bfloat16, device=dev)
+        kw.update(pre_shift=bias, relu=True, actA=ops.Act(dA))
+        checks.append(("actA", dA, torch.relu(acc + bias.double())))
+    else:
+        raise ValueError(epilogue)
+
+    ops.gemm(A, W, M=M, a_row0=a_row0, w_batched=w_batched, **kw)
+    torch.cuda.synchronize()
+
+    ok = True
+    worst = 0.0
+    for nm, got, want in checks:
+        scale = max(want.abs().max().item(), 1e-6)
+        tol = 2e-3 if got.dtype == torch.float32 else 1.2e-2  # bf16 outputs: half-ulp 2^-9 relative
+        err = (got.double() - want).abs().max().item() / scale
+        bad = not math.isfinite(err) or err > tol
+        res[nm] = err
+        worst = max(worst, err if math.isfinite(err) else float("inf"))
+        ok = ok and not bad
+    return dict(name=name, ok=ok, max_rel_err=worst, per_output=res)
+
+
+CASES = [
+    dict(name="lin_1kb", batch=1, M=256, K=64, N=128),
+    dict(name="lin_k256_n256", batch=1, M=384, K=256, N=256),
+    dict(name="lin_ragged_m", batch=2, M=300, K=128, N=192),
+    dict(name="lin_tiny_m16", batch=1, M=16, K=1536, N=1344),
+    dict(name="lin_n176", batch=1, M=128, K=192, N=1408),
+    dict(name="lin_k_tail", batch=1, M=130, K=72, N=64),
+    dict(name="conv5", batch=2, M=300, K=128, N=192, taps=5),
+    dict(name="conv5_halo", batch=2, M=256, K=128, N=128, taps=5, a_row0=2),
+    dict(name="conv5_full_epi", batch=2, M=512, K=256, N=384, taps=5, epilogue="full"),
+    dict(name="lin_relu_bf16", batch=1, M=200, K=256, N=512, epilogue="relu_bf16"),
+    dict(name="batched_w", batch=4, M=160, K=128, N=320, w_batched=True),
+    dict(name="batched_heads_strided", batch=8, M=96, K=128, N=96, w_batched=True, strided=True),
+    dict(name="persistent_many_tiles", batch=1, M=128 * 700, K=128, N=256),
+    dict(name="conv5_big", batch=1, M=16384, K=768, N=768, taps=5, epilogue="full"),
+]
