@@ -182,6 +182,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------
@@ -192,6 +201,26 @@ enum ActMode : int { ACT_NONE = 0, ACT_GELU1702 = 1, ACT_GELU_ERF = 2, ACT_RELU 
 __device__ __forceinline__ float act_apply(float x, int mode) {
   switch (mode) {
     case ACT_GELU1702: return __fdividef(x, 1.0f + __expf(-1.702f * x));
+    case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Same functions with one MUFU op where possible; used only when the result is rounded to bf16
+// (x*sigmoid(1.702x) = 0.5x + 0.5x*tanh(0.851x); tanh.approx error ~2^-11 is below bf16's 2^-9 half-ulp).
+__device__ __forceinline__ float act_apply_fast(float x, int mode) {
+  switch (mode) {
+    case ACT_GELU1702: {
+      const float hx = 0.5f * x;
+      return fmaf(hx, tanh_approx(0.851f * x), hx);
+    }
     case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     case ACT_RELU: return fmaxf(x, 0.0f);
     default: return x;

@@ -4,15 +4,16 @@
 // DNAEmbed.pointwise AG:1163, DownresBlock AG:470-481, UpresBlock AG:503-519, and the nn.Linear layers of
 // Attention / FeedForward / SingleToPairwise / PairwiseRowAttention / OutputEmbedding.
 //
-// Design (one persistent CTA per SM, 192 threads):
+// Design (one persistent CTA per SM, 320 threads):
 //   warp 0 (one lane)  TMA producer: per (tap, 64-wide K block) one A box [128 rows x 64] at row offset
 //                      tap - taps/2 (out-of-range rows are zero-filled by TMA = the conv's zero padding)
 //                      and one W box [n_tile x 64], both 128B-swizzled, into a 4-stage smem ring.
 //   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (M=128, N=n_tile, K=16) per stage, fp32 accumulators in
 //                      TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps the
 //                      mainloop of tile i+1.
-//   warps 2-5          epilogue: tcgen05.ld 32x32 blocks -> smem transpose (lane = channel) -> fused
-//                      affine / ReLU / residual / scale / activation / maxpool2 -> coalesced global stores.
+//   warps 2-9          epilogue: tcgen05.ld 32x16 blocks -> padded smem -> each lane owns 4 consecutive channels
+//                      of 4 rows -> fused affine / ReLU / residual / scale / activation / maxpool2 ->
+//                      128-bit global loads and stores.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -24,10 +25,11 @@ constexpr int kStages = 4;
 constexpr int kMaxNTile = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kBBytesMax = kMaxNTile * kBlockK * 2; // 32 KB
-constexpr int kEpiWarps = 4;
-constexpr int kEpiPad = 33;
-constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPad * 4;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiCols = 16;                          // columns per TMEM load / staged chunk
+constexpr int kEpiStride = 20;                        // floats per staged row (16 + 4 pad; 5 x 16 B, odd)
+constexpr int kEpiBytes = kEpiWarps * 32 * kEpiStride * 4;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int kGemmSmem = 1024 /*align slack*/ + kStages * (kABytes + kBBytesMax) + kEpiBytes + 256;
 
 struct GemmKParams {
@@ -38,13 +40,36 @@ struct GemmKParams {
   unsigned int* err;
 };
 
-__device__ __forceinline__ void epi_store(const AgEpiOut& o, int b, long row, int c, float v) {
-  float s = o.scale ? __ldg(o.scale + c) : 1.0f;
-  float t = o.shift ? __ldg(o.shift + (long)b * o.shift_bstride + c) : 0.0f;
-  float y = act_apply(fmaf(v, s, t), o.act);
-  long idx = (long)b * o.bstride + row * o.ld + c;
-  if (o.dtype == 0) reinterpret_cast<__nv_bfloat16*>(o.ptr)[idx] = __float2bfloat16_rn(y);
-  else reinterpret_cast<float*>(o.ptr)[idx] = y;
+// One activated output for 4 consecutive channels of one row (scale/shift pre-loaded per chunk).
+__device__ __forceinline__ void epi_store4(const AgEpiOut& o, long off, float4 v, const float4& s, const float4& t) {
+  float4 y;
+  y.x = fmaf(v.x, s.x, t.x);
+  y.y = fmaf(v.y, s.y, t.y);
+  y.z = fmaf(v.z, s.z, t.z);
+  y.w = fmaf(v.w, s.w, t.w);
+  if (o.dtype == 0) {
+    y.x = act_apply_fast(y.x, o.act);
+    y.y = act_apply_fast(y.y, o.act);
+    y.z = act_apply_fast(y.z, o.act);
+    y.w = act_apply_fast(y.w, o.act);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(y.z, y.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(o.ptr) + off) = pk;
+  } else {
+    y.x = act_apply(y.x, o.act);
+    y.y = act_apply(y.y, o.act);
+    y.z = act_apply(y.z, o.act);
+    y.w = act_apply(y.w, o.act);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.ptr) + off) = y;
+  }
+}
+
+__device__ __forceinline__ float4 ldg4_or(const float* p, long off, float dflt) {
+  if (p) return __ldg(reinterpret_cast<const float4*>(p + off));
+  return make_float4(dflt, dflt, dflt, dflt);
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
@@ -146,13 +171,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = sEpi + (warp - 2) * 32 * kEpiPad;
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter; each takes every other 16-column chunk.  Per chunk: LDTM (thread =
+    // row) -> padded smem -> each lane re-reads 4 consecutive channels of 4 rows (two adjacent-row pairs, so
+    // maxpool2 is thread-local) -> 128-bit global loads/stores.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stg = sEpi + (warp - 2) * 32 * kEpiStride;
+    const int cg = lane & 3;     // channel group: columns 4cg..4cg+3 of the chunk
+    const int rsel = lane >> 2;  // rows 2*rsel + {0,1} (+16)
     int as = 0;
     uint32_t aphase = 0;
     const float post = g.post_scale ? __ldg(g.post_scale) : 1.0f;
     const bool do_pool = (g.pool != nullptr) || (g.actP.ptr != nullptr);
+    const int nchunks = p.n_tile / kEpiCols;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
@@ -165,46 +197,60 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kMaxNTile;
 
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + (uint32_t)c0, r);
+      for (int ch = half; ch < nchunks; ch += 2) {
+        uint32_t r[16];
+        tmem_ld_32x16(t_addr + (uint32_t)(ch * kEpiCols), r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * kEpiPad + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * kEpiStride + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
 
-        const int c = n0 + c0 + lane;
-        const bool c_ok = (c0 + lane) < p.n_tile;
-        if (c_ok) {
-          const float ps = g.pre_scale ? __ldg(g.pre_scale + c) : 1.0f;
-          const float pt = g.pre_shift ? __ldg(g.pre_shift + c) : 0.0f;
-          const bool has_res = (g.res != nullptr) && (c < g.res_ch);
-          const float* resb = g.res + (long)b * g.res_bstride + c;
-#pragma unroll 4
-          for (int rp = 0; rp < 16; ++rp) {
-            float v[2];
+        const int c = n0 + ch * kEpiCols + 4 * cg;
+        const float4 ps = ldg4_or(g.pre_scale, c, 1.0f);
+        const float4 pt = ldg4_or(g.pre_shift, c, 0.0f);
+        float4 sA, tA, sB, tB, sP, tP;
+        if (g.actA.ptr) { sA = ldg4_or(g.actA.scale, c, 1.0f); tA = ldg4_or(g.actA.shift, (long)b * g.actA.shift_bstride + c, 0.0f); }
+        if (g.actB.ptr) { sB = ldg4_or(g.actB.scale, c, 1.0f); tB = ldg4_or(g.actB.shift, (long)b * g.actB.shift_bstride + c, 0.0f); }
+        if (g.actP.ptr) { sP = ldg4_or(g.actP.scale, c, 1.0f); tP = ldg4_or(g.actP.shift, (long)b * g.actP.shift_bstride + c, 0.0f); }
+        const bool has_res = (g.res != nullptr) && (c < g.res_ch);
+
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int row = r_base + 2 * rp + h;
-              float x = fmaf(stg[(2 * rp + h) * kEpiPad + lane], ps, pt);
-              if (g.relu) x = fmaxf(x, 0.0f);
-              if (row < g.M) {
-                if (has_res) x += __ldg(resb + (long)(row >> g.res_shift) * g.res_ld);
-                x *= post;
-                if (g.out) g.out[(long)b * g.out_bstride + (long)row * g.out_ld + c] = x;
-                if (g.actA.ptr) epi_store(g.actA, b, row, c, x);
-                if (g.actB.ptr) epi_store(g.actB, b, row, c, x);
+        for (int i = 0; i < 2; ++i) {
+          float4 v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int lr = 2 * rsel + h + 16 * i;
+            const int row = r_base + lr;
+            float4 x = *reinterpret_cast<const float4*>(stg + lr * kEpiStride + 4 * cg);
+            x.x = fmaf(x.x, ps.x, pt.x);
+            x.y = fmaf(x.y, ps.y, pt.y);
+            x.z = fmaf(x.z, ps.z, pt.z);
+            x.w = fmaf(x.w, ps.w, pt.w);
+            if (g.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if (row < g.M) {
+              if (has_res) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(g.res + (long)b * g.res_bstride + (long)(row >> g.res_shift) * g.res_ld + c));
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
               }
-              v[h] = x;
+              x.x *= post; x.y *= post; x.z *= post; x.w *= post;
+              if (g.out) *reinterpret_cast<float4*>(g.out + (long)b * g.out_bstride + (long)row * g.out_ld + c) = x;
+              if (g.actA.ptr) epi_store4(g.actA, (long)b * g.actA.bstride + (long)row * g.actA.ld + c, x, sA, tA);
+              if (g.actB.ptr) epi_store4(g.actB, (long)b * g.actB.bstride + (long)row * g.actB.ld + c, x, sB, tB);
             }
-            if (do_pool) {
-              const int row = r_base + 2 * rp;
-              if (row + 1 < g.M) {
-                const float pv = fmaxf(v[0], v[1]);
-                const long prow = row >> 1;
-                if (g.pool) g.pool[(long)b * g.pool_bstride + prow * g.pool_ld + c] = pv;
-                if (g.actP.ptr) epi_store(g.actP, b, prow, c, pv);
-              }
+            v[h] = x;
+          }
+          if (do_pool) {
+            const int row = r_base + 2 * rsel + 16 * i;
+            if (row + 1 < g.M) {
+              float4 pv;
+              pv.x = fmaxf(v[0].x, v[1].x);
+              pv.y = fmaxf(v[0].y, v[1].y);
+              pv.z = fmaxf(v[0].z, v[1].z);
+              pv.w = fmaxf(v[0].w, v[1].w);
+              const long prow = row >> 1;
+              if (g.pool) *reinterpret_cast<float4*>(g.pool + (long)b * g.pool_bstride + prow * g.pool_ld + c) = pv;
+              if (g.actP.ptr) epi_store4(g.actP, (long)b * g.actP.bstride + prow * g.actP.ld + c, pv, sP, tP);
             }
           }
         }
@@ -244,6 +290,23 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   if (a.w_batched && a.taps != 1) return set_error("ag_gemm_fwd: batched W requires taps == 1");
   if ((a.pool || a.actP.ptr) && (a.M & 1)) return set_error("ag_gemm_fwd: maxpool2 epilogue needs even M (got %d)", a.M);
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.W)) & 15) return set_error("ag_gemm_fwd: A/W must be 16-byte aligned");
+  // the epilogue moves 4 channels per lane with 128-bit (fp32) / 64-bit (bf16) accesses
+  if (a.res && ((a.res_ch & 3) || (a.res_ld & 3) || (a.res_bstride & 3) || (reinterpret_cast<uintptr_t>(a.res) & 15)))
+    return set_error("ag_gemm_fwd: res needs res_ch, res_ld, res_bstride multiples of 4 and a 16-byte aligned pointer");
+  if (a.out && ((a.out_ld & 3) || (a.out_bstride & 3) || (reinterpret_cast<uintptr_t>(a.out) & 15)))
+    return set_error("ag_gemm_fwd: out needs out_ld/out_bstride multiples of 4 and a 16-byte aligned pointer");
+  if (a.pool && ((a.pool_ld & 3) || (a.pool_bstride & 3) || (reinterpret_cast<uintptr_t>(a.pool) & 15)))
+    return set_error("ag_gemm_fwd: pool needs pool_ld/pool_bstride multiples of 4 and a 16-byte aligned pointer");
+  for (const AgEpiOut* o : {&a.actA, &a.actB, &a.actP}) {
+    if (!o->ptr) continue;
+    const uintptr_t al = o->dtype == 0 ? 7 : 15;
+    if ((o->ld & 3) || (o->bstride & 3) || (reinterpret_cast<uintptr_t>(o->ptr) & al) || (o->shift_bstride & 3) ||
+        (reinterpret_cast<uintptr_t>(o->scale) & 15) || (reinterpret_cast<uintptr_t>(o->shift) & 15))
+      return set_error("ag_gemm_fwd: activated outputs need ld/bstride multiples of 4 and aligned pointers");
+    if (o->dtype != 0 && o->dtype != 1) return set_error("ag_gemm_fwd: bad output dtype %d", o->dtype);
+  }
+  if ((reinterpret_cast<uintptr_t>(a.pre_scale) | reinterpret_cast<uintptr_t>(a.pre_shift)) & 15)
+    return set_error("ag_gemm_fwd: pre_scale/pre_shift must be 16-byte aligned");
 
   GemmKParams p;
   memset(&p, 0, sizeof(p));

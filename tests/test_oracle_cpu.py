@@ -1,0 +1,63 @@
+"""CPU: the oracle restatement (oracle/trunk_oracle.py) against golden outputs of the unmodified reference
+(tests/golden/*.npz, produced by tools/make_golden.py).  This is what 'pins' the oracle."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from alphagenome_b200.init_weights import synth_state_dict
+from oracle import trunk_oracle as O
+from tests.golden_util import CASES, make_inputs, sample_rows
+
+GOLD = Path(__file__).resolve().parent / "golden"
+OUTPUTS = ["embeds_1bp", "embeds_128bp", "embeds_pair", "unet_output", "single_repr", "pairwise_repr"]
+
+
+def reference_shapes():
+    shapes = {}
+    for line in (GOLD / "state_dict_keys.txt").read_text().splitlines():
+        m = re.match(r"(\S+) \((.*)\)", line)
+        dims = tuple(int(x) for x in m.group(2).replace(",", " ").split())
+        shapes[m.group(1)] = dims
+    return shapes
+
+
+def synth_sd(seed):
+    shapes = {k: v for k, v in reference_shapes().items() if not k.endswith("rel_pos_features.dummy")}
+    sd = synth_state_dict(shapes, seed)
+    sd["transformer_unet.transformer.rotary_emb.inv_freq"] = O.rotary_inv_freq(128)
+    return sd
+
+
+def test_reference_key_contract():
+    shapes = reference_shapes()
+    assert len(shapes) == 559  # head-less AlphaGenome state_dict
+    assert shapes["transformer_unet.transformer.layers.0.2.to_qk.weight"] == (8192, 1536)
+    assert shapes["transformer_unet.ups.6.conv_out.net.2.weight"] == (768, 768, 5)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_oracle_matches_reference_golden(case):
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    g = np.load(GOLD / f"{case['name']}.npz")
+    seq, org = make_inputs(case)
+    assert np.array_equal(g["seq"].astype(np.int64), seq.numpy())
+    out = O.alphagenome_embeds(synth_sd(case["weight_seed"]), seq, org)
+    for name in OUTPUTS:
+        got = out[name]
+        idx = sample_rows(name, got.shape)
+        got = (got if idx is None else got[:, idx]).numpy()
+        want = g[name]
+        scale = float(g[name + "__absmax"])
+        err = np.abs(got - want).max() / scale
+        # fp32 summation-order noise only (measured ~1e-6); 2e-5 still fails on any semantic difference
+        assert err < 2e-5, (name, err)
+
+
+def test_seed42_input_is_reference_fixture():
+    # tests/regression_data/input_sequence.npy of the reference == default_rng(42).integers(0, 4, (1, 2048))
+    seq, org = make_inputs(CASES[0])
+    assert seq.shape == (1, 2048) and int(org[0]) == 0
+    assert seq[0, :8].tolist() == np.random.default_rng(42).integers(0, 4, size=(1, 2048))[0, :8].tolist()
