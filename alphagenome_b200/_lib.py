@@ -42,6 +42,8 @@ class AgGemmArgs(C.Structure):
         ("N", C.c_int32),
         ("K", C.c_int32),
         ("taps", C.c_int32),
+        ("w_rows", C.c_int32),
+        ("reserved0", C.c_int32),
         ("pre_scale", C.c_void_p),
         ("pre_shift", C.c_void_p),
         ("relu", C.c_int32),
@@ -63,6 +65,42 @@ class AgGemmArgs(C.Structure):
     ]
 
 
+class AgAttnArgs(C.Structure):
+    _fields_ = [
+        ("Q", C.c_void_p),
+        ("K", C.c_void_p),
+        ("Vt", C.c_void_p),
+        ("q_bstride", C.c_int64),
+        ("q_hstride", C.c_int64),
+        ("k_bstride", C.c_int64),
+        ("k_hstride", C.c_int64),
+        ("v_bstride", C.c_int64),
+        ("v_hstride", C.c_int64),
+        ("q_ld", C.c_int32),
+        ("k_ld", C.c_int32),
+        ("v_ld", C.c_int32),
+        ("batch", C.c_int32),
+        ("heads", C.c_int32),
+        ("kv_heads", C.c_int32),
+        ("n_q", C.c_int32),
+        ("n_k", C.c_int32),
+        ("d", C.c_int32),
+        ("dv", C.c_int32),
+        ("mode", C.c_int32),
+        ("bias_p", C.c_int32),
+        ("scale", C.c_float),
+        ("softcap", C.c_float),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p),
+        ("out_bstride", C.c_int64),
+        ("out_hstride", C.c_int64),
+        ("out_ld", C.c_int32),
+        ("out_dtype", C.c_int32),
+        ("out_bias", C.c_void_p),
+        ("res", C.c_void_p),
+    ]
+
+
 ACT_NONE, ACT_GELU1702, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
 
 # every symbol include/agb200.h declares; tests check the built library exports all of them
@@ -73,6 +111,16 @@ EXPORTED = [
     "ag_check_device",
     "ag_watchdog_status",
     "ag_gemm_fwd",
+    "ag_attention_fwd",
+    "ag_onehot_im2col_fwd",
+    "ag_qkv_post_fwd",
+    "ag_transpose_bf16",
+    "ag_pair_bias_fwd",
+    "ag_pool_rmsnorm_fwd",
+    "ag_pair_combine_fwd",
+    "ag_rmsnorm_fwd",
+    "ag_add_embed_norm_fwd",
+    "ag_pair_out_embed_fwd",
 ]
 
 _lib = None
@@ -102,6 +150,19 @@ def load() -> C.CDLL:
     lib.ag_watchdog_status.restype = C.c_int
     lib.ag_gemm_fwd.argtypes = [C.POINTER(AgGemmArgs), C.c_int, C.c_void_p]
     lib.ag_gemm_fwd.restype = C.c_int
+    P, I32, I64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.ag_attention_fwd.argtypes = [C.POINTER(AgAttnArgs), C.c_int, P]
+    lib.ag_onehot_im2col_fwd.argtypes = [P, P, I32, I32, I32, I32, I32, C.c_int, P]
+    lib.ag_qkv_post_fwd.argtypes = [P] * 12 + [I32] * 5 + [C.c_int, P]
+    lib.ag_transpose_bf16.argtypes = [P, P, I32, I32, I32, I64, I32, I64, I32, C.c_int, P]
+    lib.ag_pair_bias_fwd.argtypes = [P] * 5 + [I32] * 4 + [C.c_int, P]
+    lib.ag_pool_rmsnorm_fwd.argtypes = [P] * 5 + [I32] * 4 + [C.c_int, P]
+    lib.ag_pair_combine_fwd.argtypes = [P] * 8 + [I32] * 6 + [C.c_int, P]
+    lib.ag_rmsnorm_fwd.argtypes = [P] * 4 + [I64, I32, C.c_int, P]
+    lib.ag_add_embed_norm_fwd.argtypes = [P] * 6 + [I32] * 3 + [C.c_int, P]
+    lib.ag_pair_out_embed_fwd.argtypes = [P] * 5 + [I32] * 3 + [C.c_int, P]
+    for name in EXPORTED[5:]:
+        getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
 

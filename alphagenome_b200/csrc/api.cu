@@ -135,4 +135,71 @@ int ag_gemm_fwd(const AgGemmArgs* args, int device, void* stream) {
   return launch_gemm(*args, device, static_cast<cudaStream_t>(stream));
 }
 
+int ag_attention_fwd(const AgAttnArgs* args, int device, void* stream) {
+  if (!args) return set_error("ag_attention_fwd: null args");
+  if (int rc = ensure_device(device)) return rc;
+  return launch_attention(*args, device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_onehot_im2col_fwd(const int64_t* tokens, void* out_bf16, int32_t B, int32_t L, int32_t width, int32_t n_base,
+                         int32_t ld, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_onehot_im2col(tokens, out_bf16, B, L, width, n_base, ld, device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_qkv_post_fwd(const float* qkv, void* Q, void* K, void* V, const float* cos_tab, const float* sin_tab,
+                    const float* q_w, const float* q_b, const float* k_w, const float* k_b, const float* v_w,
+                    const float* v_b, int32_t B, int32_t n, int32_t heads, int32_t d, int32_t dv, int device,
+                    void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_qkv_post(qkv, Q, K, V, cos_tab, sin_tab, q_w, q_b, k_w, k_b, v_w, v_b, B, n, heads, d, dv, device,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t C, int64_t in_bstride, int32_t in_ld,
+                      int64_t out_bstride, int32_t out_ld, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_transpose_bf16(in, out, nb, R, C, in_bstride, in_ld, out_bstride, out_ld, device,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int ag_pair_bias_fwd(const float* pair, const float* scale, const float* shift, const float* W, float* bias, int32_t B,
+                     int32_t P, int32_t C, int32_t heads, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_pair_bias(pair, scale, shift, W, bias, B, P, C, heads, device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_pool_rmsnorm_fwd(const float* single, const float* w, const float* b, void* x_bf16, void* xg_bf16, int32_t B,
+                        int32_t n, int32_t C, int32_t pool, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_pool_rmsnorm(single, w, b, x_bf16, xg_bf16, B, n, C, pool, device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_pair_combine_fwd(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
+                        const float* outer, const float* prev, float* pair, int32_t B, int32_t P, int32_t H, int32_t D,
+                        int32_t qk_ld, int32_t rel_ld, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair, B, P, H, D, qk_ld, rel_ld, device,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int ag_rmsnorm_fwd(const float* x, const float* w, const float* b, void* out_bf16, int64_t rows, int32_t C, int device,
+                   void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_rmsnorm(x, w, b, out_bf16, rows, C, device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_add_embed_norm_fwd(const float* x, const float* emb, const float* scale, const float* shift, float* single,
+                          void* a_bf16, int32_t B, int32_t rows, int32_t C, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_add_embed_norm(x, emb, scale, shift, single, a_bf16, B, rows, C, device,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int ag_pair_out_embed_fwd(const float* pair, const float* w, const float* b, const float* emb, float* out, int32_t B,
+                          int32_t P, int32_t C, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_pair_out_embed(pair, w, b, emb, out, B, P, C, device, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

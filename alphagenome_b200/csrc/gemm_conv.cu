@@ -288,6 +288,7 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
     return set_error("ag_gemm_fwd: K, a_ld, w_ld and strides must be multiples of 8 (16-byte TMA alignment)");
   if ((a.taps & 1) == 0 || a.taps < 1 || a.taps > 15) return set_error("ag_gemm_fwd: taps=%d must be odd and <= 15", a.taps);
   if (a.w_batched && a.taps != 1) return set_error("ag_gemm_fwd: batched W requires taps == 1");
+  if (a.w_rows < 0 || a.w_rows > a.N) return set_error("ag_gemm_fwd: w_rows=%d out of range", a.w_rows);
   if ((a.pool || a.actP.ptr) && (a.M & 1)) return set_error("ag_gemm_fwd: maxpool2 epilogue needs even M (got %d)", a.M);
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.W)) & 15) return set_error("ag_gemm_fwd: A/W must be 16-byte aligned");
   // the epilogue moves 4 channels per lane with 128-bit (fp32) / 64-bit (bf16) accesses
@@ -327,8 +328,8 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   }
   {
     const int nz = a.w_batched ? a.batch : a.taps;
-    uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, (uint64_t)nz};
-    uint64_t strides[2] = {(uint64_t)a.w_ld * 2, (uint64_t)(nz > 1 ? a.w_zstride : (int64_t)a.w_ld * a.N) * 2};
+    uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)(a.w_rows > 0 ? a.w_rows : a.N), (uint64_t)nz};
+    uint64_t strides[2] = {(uint64_t)a.w_ld * 2, (uint64_t)(nz > 1 ? a.w_zstride : (int64_t)a.w_ld * (a.w_rows > 0 ? a.w_rows : a.N)) * 2};
     uint32_t box[3] = {kBlockK, (uint32_t)p.n_tile, 1};
     if (int rc = make_tensor_map_bf16(&p.tmB, a.W, 3, dims, strides, box)) return rc;
   }

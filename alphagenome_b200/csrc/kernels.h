@@ -21,5 +21,26 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
                          const uint64_t* strides_bytes, const uint32_t* box);
 
 int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream);
+int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream);
+int launch_onehot_im2col(const int64_t* tokens, void* out, int B, int L, int width, int n_base, int ld, int device,
+                         cudaStream_t st);
+int launch_qkv_post(const float* qkv, void* Q, void* K, void* V, const float* cos_tab, const float* sin_tab,
+                    const float* q_w, const float* q_b, const float* k_w, const float* k_b, const float* v_w,
+                    const float* v_b, int B, int n, int heads, int d, int dv, int device, cudaStream_t st);
+int launch_transpose_bf16(const void* in, void* out, int nb, int R, int C, long in_bs, int in_ld, long out_bs,
+                          int out_ld, int device, cudaStream_t st);
+int launch_pair_bias(const float* pair, const float* scale, const float* shift, const float* W, float* bias, int B,
+                     int P, int C, int heads, int device, cudaStream_t st);
+int launch_pool_rmsnorm(const float* single, const float* w, const float* b, void* x, void* xg, int B, int n, int C,
+                        int pool, int device, cudaStream_t st);
+int launch_pair_combine(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
+                        const float* outer, const float* prev, float* pair, int B, int P, int H, int D, int qk_ld,
+                        int rel_ld, int device, cudaStream_t st);
+int launch_rmsnorm(const float* x, const float* w, const float* b, void* out, long rows, int C, int device,
+                   cudaStream_t st);
+int launch_add_embed_norm(const float* x, const float* emb, const float* scale, const float* shift, float* single,
+                          void* a, int B, int rows, int C, int device, cudaStream_t st);
+int launch_pair_out_embed(const float* pair, const float* w, const float* b, const float* emb, float* out, int B, int P,
+                          int C, int device, cudaStream_t st);
 
 }  // namespace agb

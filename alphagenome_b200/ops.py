@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU1702, ACT_GELU_ERF, ACT_NONE, ACT_RELU, AgEpiOut, AgGemmArgs  # noqa: F401
+from ._lib import ACT_GELU1702, ACT_GELU_ERF, ACT_NONE, ACT_RELU, AgAttnArgs, AgEpiOut, AgGemmArgs  # noqa: F401
 
 
 @dataclass
@@ -78,6 +78,7 @@ def gemm(
     M: Optional[int] = None,
     a_row0: int = 0,
     w_batched: bool = False,
+    n_pad: Optional[int] = None,
     pre_scale: Optional[torch.Tensor] = None,
     pre_shift: Optional[torch.Tensor] = None,
     relu: bool = False,
@@ -107,6 +108,11 @@ def gemm(
         _require(W.shape[0] == batch, "batched W needs W.shape[0] == batch")
     if M is None:
         M = a_rows - 2 * a_row0
+    w_rows = 0
+    if n_pad is not None and n_pad != N:
+        # W has fewer rows than the (16-aligned) N the kernel computes; the missing rows read as zero
+        _require(n_pad > N and n_pad % 16 == 0, "n_pad must be a multiple of 16 and >= W rows")
+        w_rows, N = N, n_pad
 
     g = AgGemmArgs()
     g.A = A.data_ptr()
@@ -119,6 +125,7 @@ def gemm(
     g.w_zstride = W.stride(0)
     g.w_ld = W.stride(1)
     g.batch, g.M, g.N, g.K, g.taps = batch, M, N, K, taps
+    g.w_rows = w_rows
     for name, v in (("pre_scale", pre_scale), ("pre_shift", pre_shift)):
         if v is not None:
             _require(v.dtype == torch.float32 and v.numel() == N and v.is_contiguous(), f"{name} must be fp32 [N]")
@@ -159,3 +166,139 @@ def gemm(
     _fill_act(g.actB, actB, batch, M, N)
     _fill_act(g.actP, actP, batch, M // 2, N)
     _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
+
+
+def _dev(t: torch.Tensor) -> int:
+    return t.device.index or 0
+
+
+def _f32(t: Optional[torch.Tensor], name: str) -> None:
+    if t is not None:
+        _require(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), f"{name} must be a contiguous CUDA fp32 tensor")
+
+
+def attention(
+    Q: torch.Tensor,
+    K: torch.Tensor,
+    Vt: torch.Tensor,
+    out: torch.Tensor,
+    *,
+    mode: int,
+    scale: float,
+    bias: Optional[torch.Tensor] = None,
+    softcap: float = 5.0,
+    out_bias: Optional[torch.Tensor] = None,
+    res: Optional[torch.Tensor] = None,
+) -> None:
+    """ag_attention_fwd.  Q [B, H, n_q, d], K [B, Hk, n_k, d], Vt [B, Hk, dv, n_k(+pad)] (bf16 views, last dim
+    contiguous), out [B, H, n_q, dv] (bf16 or fp32 view).  n_k is taken from K."""
+    lib = _lib.load()
+    for t, nm in ((Q, "Q"), (K, "K"), (Vt, "Vt")):
+        _require(t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4 and t.stride(3) == 1, f"{nm} must be a 4-d CUDA bf16 view")
+    B, H, n_q, d = Q.shape
+    Hk, n_k = K.shape[1], K.shape[2]
+    dv = Vt.shape[2]
+    _require(K.shape[0] == B and K.shape[3] == d and Vt.shape[0] == B and Vt.shape[1] == Hk and Vt.shape[3] >= n_k, "K/Vt shape mismatch")
+    _require(out.dim() == 4 and tuple(out.shape) == (B, H, n_q, dv) and out.stride(3) == 1, f"out must be [B,H,n_q,dv], got {tuple(out.shape)}")
+    a = AgAttnArgs()
+    a.Q, a.K, a.Vt = Q.data_ptr(), K.data_ptr(), Vt.data_ptr()
+    a.q_bstride, a.q_hstride, a.q_ld = Q.stride(0), Q.stride(1), Q.stride(2)
+    a.k_bstride, a.k_hstride, a.k_ld = K.stride(0), K.stride(1), K.stride(2)
+    a.v_bstride, a.v_hstride, a.v_ld = Vt.stride(0), Vt.stride(1), Vt.stride(2)
+    a.batch, a.heads, a.kv_heads, a.n_q, a.n_k, a.d, a.dv = B, H, Hk, n_q, n_k, d, dv
+    a.mode = mode
+    a.scale, a.softcap = float(scale), float(softcap)
+    if bias is not None:
+        _f32(bias, "bias")
+        _require(bias.dim() == 4 and bias.shape[0] == B and bias.shape[1] == H and bias.shape[2] == bias.shape[3], "bias must be [B,H,P,P]")
+        a.bias, a.bias_p = bias.data_ptr(), bias.shape[2]
+    a.out = out.data_ptr()
+    a.out_bstride, a.out_hstride, a.out_ld = out.stride(0), out.stride(1), out.stride(2)
+    a.out_dtype = 0 if out.dtype == torch.bfloat16 else 1
+    _f32(out_bias, "out_bias")
+    a.out_bias = _ptr(out_bias)
+    if res is not None:
+        _require(res.dtype == torch.float32 and res.shape == out.shape and res.stride() == out.stride(), "res must match out's layout")
+    a.res = _ptr(res)
+    _lib.check(lib.ag_attention_fwd(C.byref(a), _dev(Q), _stream()))
+
+
+def onehot_im2col(tokens: torch.Tensor, out: torch.Tensor, width: int, n_base: int) -> None:
+    _require(tokens.is_cuda and tokens.dtype == torch.int64 and tokens.is_contiguous() and tokens.dim() == 2, "tokens must be CUDA int64 [B, L]")
+    B, L = tokens.shape
+    _require(out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape[:2]) == (B, L), "out must be bf16 [B, L, ld]")
+    _lib.check(_lib.load().ag_onehot_im2col_fwd(tokens.data_ptr(), out.data_ptr(), B, L, width, n_base, out.shape[2], _dev(out), _stream()))
+
+
+def qkv_post(qkv, Q, K, V, cos_tab, sin_tab, qw, qb, kw, kb, vw, vb, heads: int, d: int, dv: int) -> None:
+    B, n, Ctot = qkv.shape
+    _require(Ctot == heads * d + d + dv, "qkv channel count mismatch")
+    for t, nm in ((qkv, "qkv"), (cos_tab, "cos"), (sin_tab, "sin"), (qw, "qw"), (qb, "qb"), (kw, "kw"), (kb, "kb"), (vw, "vw"), (vb, "vb")):
+        _f32(t, nm)
+    _require(cos_tab.shape[0] >= n and cos_tab.shape[1] == d // 2, "rope tables must be [>=n, d/2]")
+    for t in (Q, K, V):
+        _require(t.dtype == torch.bfloat16 and t.is_contiguous(), "Q/K/V outputs must be contiguous bf16")
+    _lib.check(_lib.load().ag_qkv_post_fwd(qkv.data_ptr(), Q.data_ptr(), K.data_ptr(), V.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(),
+                                           qw.data_ptr(), qb.data_ptr(), kw.data_ptr(), kb.data_ptr(), vw.data_ptr(), vb.data_ptr(),
+                                           B, n, heads, d, dv, _dev(qkv), _stream()))
+
+
+def transpose_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[b, c, r] = src[b, r, c]; src [nb, R, C] bf16 view, dst [nb, C, >=R] bf16 view (last dims contiguous)."""
+    _require(src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.dim() == 3 and dst.dim() == 3, "bf16 3-d views expected")
+    nb, R, Cc = src.shape
+    _require(dst.shape[0] == nb and dst.shape[1] == Cc and dst.shape[2] >= R and src.stride(2) == 1 and dst.stride(2) == 1, "transpose shape mismatch")
+    _lib.check(_lib.load().ag_transpose_bf16(src.data_ptr(), dst.data_ptr(), nb, R, Cc, src.stride(0), src.stride(1), dst.stride(0), dst.stride(1), _dev(src), _stream()))
+
+
+def pair_bias(pair, scale, shift, W, bias_out) -> None:
+    B, P, _, Cc = pair.shape
+    for t, nm in ((pair, "pair"), (scale, "scale"), (shift, "shift"), (W, "W"), (bias_out, "bias_out")):
+        _f32(t, nm)
+    heads = W.shape[0]
+    _require(tuple(bias_out.shape) == (B, heads, P, P), "bias_out must be [B, heads, P, P]")
+    _lib.check(_lib.load().ag_pair_bias_fwd(pair.data_ptr(), scale.data_ptr(), shift.data_ptr(), W.data_ptr(), bias_out.data_ptr(), B, P, Cc, heads, _dev(pair), _stream()))
+
+
+def pool_rmsnorm(single, w, b, x_out, xg_out, pool: int) -> None:
+    B, n, Cc = single.shape
+    for t, nm in ((single, "single"), (w, "w"), (b, "b")):
+        _f32(t, nm)
+    for t in (x_out, xg_out):
+        _require(t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == (B, n // pool, Cc), "pooled outputs must be bf16 [B, n/pool, C]")
+    _lib.check(_lib.load().ag_pool_rmsnorm_fwd(single.data_ptr(), w.data_ptr(), b.data_ptr(), x_out.data_ptr(), xg_out.data_ptr(), B, n, Cc, pool, _dev(single), _stream()))
+
+
+def pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair_out, P: int) -> None:
+    B, H = qk.shape[0], qk.shape[1]
+    D = Wp.shape[0]
+    for t, nm in ((qk, "qk"), (relq, "relq"), (relk, "relk"), (Wp, "Wp"), (bp, "bp"), (outer, "outer"), (prev, "prev"), (pair_out, "pair_out")):
+        _f32(t, nm)
+    _require(tuple(qk.shape[:3]) == (B, H, P) and tuple(relq.shape[:3]) == (B, H, P) and relk.shape == relq.shape, "qk/relq/relk must be [B,H,P,ld]")
+    _require(tuple(outer.shape) == (B, P, 2 * D) and tuple(pair_out.shape) == (B, P, P, D), "outer/pair_out shape mismatch")
+    _lib.check(_lib.load().ag_pair_combine_fwd(qk.data_ptr(), relq.data_ptr(), relk.data_ptr(), Wp.data_ptr(), bp.data_ptr(), outer.data_ptr(),
+                                               _ptr(prev), pair_out.data_ptr(), B, P, H, D, qk.shape[3], relq.shape[3], _dev(qk), _stream()))
+
+
+def rmsnorm(x, w, b, out) -> None:
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    for t, nm in ((x, "x"), (w, "w"), (b, "b")):
+        _f32(t, nm)
+    _require(out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() == x.numel(), "out must be contiguous bf16 of x's size")
+    _lib.check(_lib.load().ag_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, Cc, _dev(x), _stream()))
+
+
+def add_embed_norm(x, emb, scale, shift, single_out, a_out) -> None:
+    B, rows, Cc = x.shape
+    for t, nm in ((x, "x"), (emb, "emb"), (scale, "scale"), (shift, "shift"), (single_out, "single_out")):
+        _f32(t, nm)
+    _require(tuple(emb.shape) == (B, Cc) and a_out.dtype == torch.bfloat16 and a_out.is_contiguous(), "emb must be [B, C]; a_out bf16")
+    _lib.check(_lib.load().ag_add_embed_norm_fwd(x.data_ptr(), emb.data_ptr(), scale.data_ptr(), shift.data_ptr(), single_out.data_ptr(), a_out.data_ptr(), B, rows, Cc, _dev(x), _stream()))
+
+
+def pair_out_embed(pair, w, b, emb, out) -> None:
+    B, P, _, Cc = pair.shape
+    for t, nm in ((pair, "pair"), (w, "w"), (b, "b"), (emb, "emb"), (out, "out")):
+        _f32(t, nm)
+    _lib.check(_lib.load().ag_pair_out_embed_fwd(pair.data_ptr(), w.data_ptr(), b.data_ptr(), emb.data_ptr(), out.data_ptr(), B, P, Cc, _dev(pair), _stream()))

@@ -1,0 +1,423 @@
+"""Fused trunk engine: schedules the libagb200 kernels for TransformerUnet.forward (AG:1095-1136) and the
+output embeddings (AG:1754-1778).  AG = reference alphagenome_pytorch/alphagenome.py.
+
+Data layout in HBM (B = batch, len = positions at the current resolution, C = channels):
+  * activations are channels-last [B, len, C];
+  * the residual stream is fp32; every tensor-core operand is a bf16 tensor that was produced *already
+    normalised and activated* (BatchRMSNorm affine + GELU1702 of the consumer) by the epilogue of the kernel
+    that produced the residual — so a conv's zero padding (AG:448) is TMA out-of-bounds fill and no
+    activation is ever re-read just to normalise it;
+  * the U-Net skips are never stored raw: the encoder epilogue writes gelu(norm_unet(skip)) in bf16, the
+    only form UpresBlock.unet_conv consumes (AG:517);
+  * the pair tensor is fp32 [B, P, P, 128]; attention logits are never materialised.
+
+Weights are packed once per parameter version (bf16, [taps][C_out][C_in]; norms folded to per-channel
+(scale, shift) vectors) and cached on the engine.
+"""
+from __future__ import annotations
+
+import math
+import weakref
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU1702, ACT_GELU_ERF, ACT_NONE, Act
+
+_ENGINES: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def engine_for(unet, model=None) -> "TrunkEngine":
+    eng = _ENGINES.get(unet)
+    if eng is None:
+        eng = TrunkEngine(unet)
+        _ENGINES[unet] = eng
+    if model is not None:
+        eng.model = weakref.ref(model)
+    return eng
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class TrunkEngine:
+    def __init__(self, unet):
+        self.unet = weakref.ref(unet)
+        self.model = None
+        self._pack: Optional[Dict] = None
+        self._pack_key = None
+        self._rope: Dict = {}
+        self._rel: Dict = {}
+        self.collect = None  # optional callback(name, tensor) for per-stage parity tests
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _version_key(self, device):
+        unet = self.unet()
+        mods = [unet] + ([self.model()] if self.model is not None and self.model() is not None else [])
+        key = [str(device)]
+        for m in mods:
+            for t in list(m.parameters()) + list(m.buffers()):
+                key.append((t.data_ptr(), t._version))
+        return tuple(key)
+
+    def pack(self, device) -> Dict:
+        key = self._version_key(device)
+        if self._pack is not None and self._pack_key == key:
+            return self._pack
+        unet = self.unet()
+        if device.type != "cuda":
+            raise ops._lib.AgbError("alphagenome_b200 runs only on a CUDA (sm_100a) device; move the model and inputs to cuda")
+        f32 = dict(device=device, dtype=torch.float32)
+
+        def vec(t):
+            return t.detach().to(**f32).contiguous()
+
+        def wconv(conv):  # [Co, Ci, taps] -> bf16 [taps, Co, Ci]
+            return conv.weight.detach().to(device).permute(2, 0, 1).contiguous().to(torch.bfloat16)
+
+        def wlin(lin):  # [N, K] -> bf16 [1, N, K]
+            return lin.weight.detach().to(device).to(torch.bfloat16).contiguous().unsqueeze(0)
+
+        def aff(norm):
+            s, t = norm.affine()
+            return vec(s), vec(t)
+
+        def convblock(cb):
+            s, t = aff(cb.norm)
+            return dict(W=wconv(cb.conv), b=vec(cb.conv.bias), s=s, t=t)
+
+        P: Dict = {}
+        de = unet.dna_embed
+        C0, nb, width = de.conv.weight.shape
+        k_emb = _round_up(width * nb, 64)
+        w15 = torch.zeros(C0, k_emb, device=device, dtype=torch.float32)
+        # im2col column t*n_base + base  <-  conv.weight[c, base, t]
+        w15[:, : width * nb] = de.conv.weight.detach().to(device).permute(0, 2, 1).reshape(C0, width * nb)
+        P["embed"] = dict(W=w15.to(torch.bfloat16).unsqueeze(0).contiguous(), b=vec(de.conv.bias), width=width, n_base=nb, K=k_emb)
+        P["pointwise"] = convblock(de.pointwise)
+        P["downs"] = [dict(conv=convblock(d.conv), conv_out=convblock(d.conv_out)) for d in unet.downs]
+        P["ups"] = [dict(conv=convblock(u.conv), unet_conv=convblock(u.unet_conv), conv_out=convblock(u.conv_out),
+                         scale=vec(u.residual_scale)) for u in unet.ups]
+
+        tw = unet.transformer
+        layers = []
+        for attn_w, ff_w, s2p, pattn_w, pff_w in tw.layers:
+            L: Dict = {}
+            at = attn_w.block
+            s_pre, t_pre = aff(attn_w.pre_rmsnorm)
+            s_post, t_post = aff(attn_w.post_rmsnorm)
+            ab_s, ab_t = aff(at.to_attn_bias[0])
+            L["attn"] = dict(
+                pre=(s_pre, t_pre), Wqkv=wlin(at.to_qkv), Wout=wlin(at.to_out),
+                out_scale=s_post.clone(), out_shift=(vec(at.to_out.bias) * s_post + t_post).contiguous(),
+                qw=vec(at.q_norm.weight), qb=vec(at.q_norm.bias), kw=vec(at.k_norm.weight), kb=vec(at.k_norm.bias),
+                vw=vec(at.v_norm.weight), vb=vec(at.v_norm.bias), ab_s=ab_s, ab_t=ab_t, ab_W=vec(at.to_attn_bias[2].weight),
+                heads=at.heads, d=at.dim_head_qk, dv=at.dim_head_v, scale=at.scale, softcap=at.softclamp_value)
+            fs_pre, ft_pre = aff(ff_w.pre_rmsnorm)
+            fs_post, ft_post = aff(ff_w.post_rmsnorm)
+            L["ff"] = dict(pre=(fs_pre, ft_pre), W1=wlin(ff_w.block[0]), b1=vec(ff_w.block[0].bias), W2=wlin(ff_w.block[3]),
+                           out_scale=fs_post.clone(), out_shift=(vec(ff_w.block[3].bias) * fs_post + ft_post).contiguous())
+            if s2p is not None:
+                H, dp = s2p.heads, s2p.dim_pairwise
+                L["s2p"] = dict(
+                    nw=vec(s2p.norm.weight), nb=vec(s2p.norm.bias), Wqk=wlin(s2p.to_qk), Wouter=wlin(s2p.to_outer_sum[1]),
+                    relbias=vec(s2p.qk_rel_pos_bias.reshape(-1)), Wp=vec(s2p.qk_to_pairwise.weight), bp=vec(s2p.qk_to_pairwise.bias),
+                    Wrel=wlin(s2p.to_rel_pos_encoding), brel=vec(s2p.to_rel_pos_encoding.bias), heads=H, dp=dp, pool=s2p.pool_size)
+                pa = pattn_w.block
+                L["pattn"] = dict(nw=vec(pattn_w.pre_rmsnorm.weight), nb=vec(pattn_w.pre_rmsnorm.bias), Wqk=wlin(pa.to_qk),
+                                  Wv=wlin(pa.to_v), bv=vec(pa.to_v.bias), scale=pa.scale)
+                L["pff"] = dict(nw=vec(pff_w.pre_rmsnorm.weight), nb=vec(pff_w.pre_rmsnorm.bias), W1=wlin(pff_w.block[0]),
+                                b1=vec(pff_w.block[0].bias), W2=wlin(pff_w.block[3]), b2=vec(pff_w.block[3].bias))
+            layers.append(L)
+        P["layers"] = layers
+        P["inv_freq"] = tw.rotary_emb.inv_freq.detach().float().cpu()
+
+        model = self.model() if self.model is not None else None
+        if model is not None:
+            def outemb(oe):
+                s, t = aff(oe.norm)
+                # per-organism shift table: norm shift + organism embedding (AG:1231-1233)
+                table = (t[None, :] + vec(oe.embed.weight)).contiguous()
+                return dict(W=wlin(oe.double_features), b=vec(oe.double_features.bias), s=s, table=table,
+                            Wskip=wlin(oe.skip_proj) if oe.skip_proj is not None else None)
+
+            P["out128"] = outemb(model.outembed_128bp)
+            P["out1"] = outemb(model.outembed_1bp)
+            P["outpair"] = dict(w=vec(model.outembed_pair.norm.weight), b=vec(model.outembed_pair.norm.bias),
+                                emb=vec(model.outembed_pair.embed.weight))
+            P["org"] = vec(model.organism_embed.embed.weight)
+        self._pack, self._pack_key = P, key
+        self._rel.clear()
+        return P
+
+    def rope_tables(self, n: int, device, offset: int = 0):
+        key = (n, offset, str(device))
+        if key not in self._rope:
+            inv = self._pack["inv_freq"]
+            ang = torch.arange(offset, offset + n, dtype=torch.float32)[:, None] * inv[None, :]  # AG:555-556
+            self._rope[key] = (ang.cos().to(device).contiguous(), ang.sin().to(device).contiguous())
+        return self._rope[key]
+
+    def rel_encoding(self, li: int, Pn: int, device):
+        """R = to_rel_pos_encoding(features) for 2P relative distances (AG:838-839): bf16 [2P, H*dp]; data-independent."""
+        key = (li, Pn)
+        if key not in self._rel:
+            sp = self._pack["layers"][li]["s2p"]
+            feats = self.unet().transformer.rel_pos_features.features(Pn).to(device).to(torch.bfloat16).contiguous()  # exact 0/+-1
+            R = torch.empty(1, 2 * Pn, sp["heads"] * sp["dp"], device=device, dtype=torch.bfloat16)
+            ops.gemm(feats.unsqueeze(0), sp["Wrel"], pre_shift=sp["brel"], actA=Act(R))
+            self._rel[key] = R[0]
+        return self._rel[key]
+
+    # ------------------------------------------------------------------------------------------ forward pieces
+    def _note(self, name, t):
+        if self.collect is not None:
+            self.collect(name, t)
+
+    def _encoder(self, P, seq):
+        B, L = seq.shape
+        dev = seq.device
+        unet = self.unet()
+        n_down = len(P["downs"])
+        if L % (2 ** (n_down + 1) * 16) != 0:
+            raise ops._lib.AgbError(f"sequence length {L} must be a multiple of {2 ** (n_down + 1) * 16} (pool 2^{n_down + 1}, then 16)")
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        e = P["embed"]
+        C0 = unet.dims[0]
+        X = torch.empty(B, L, e["K"], **bf)
+        ops.onehot_im2col(seq, X, e["width"], e["n_base"])
+        pw = P["pointwise"]
+        x0 = torch.empty(B, L, C0, **f32)
+        a0 = torch.empty(B, L, C0, **bf)
+        ops.gemm(X, e["W"], pre_shift=e["b"], out=x0, actA=Act(a0, pw["s"], pw["t"], ACT_GELU1702))
+        del X
+        ups = P["ups"]
+        skips = [None] * (n_down + 1)  # skips[j] feeds ups[j]
+        un = ups[n_down]["unet_conv"]
+        skips[n_down] = torch.empty(B, L, C0, **bf)
+        x = torch.empty(B, L // 2, C0, **f32)
+        a = torch.empty(B, L // 2, C0, **bf)
+        d0 = P["downs"][0]["conv"]
+        ops.gemm(a0, pw["W"], pre_shift=pw["b"], res=x0, actA=Act(skips[n_down], un["s"], un["t"], ACT_GELU1702),
+                 pool=x, actP=Act(a, d0["s"], d0["t"], ACT_GELU1702))
+        del x0, a0
+        self._note("embed.pooled", x)
+        length = L // 2
+        for i, d in enumerate(P["downs"]):
+            c, co = d["conv"], d["conv_out"]
+            C_in, C_out = c["W"].shape[2], c["W"].shape[1]
+            y1 = torch.empty(B, length, C_out, **f32)
+            ay1 = torch.empty(B, length, C_out, **bf)
+            ops.gemm(a, c["W"], pre_shift=c["b"], res=x, res_ch=C_in, out=y1, actA=Act(ay1, co["s"], co["t"], ACT_GELU1702))
+            j = n_down - 1 - i
+            un = ups[j]["unet_conv"]
+            skips[j] = torch.empty(B, length, C_out, **bf)
+            xn = torch.empty(B, length // 2, C_out, **f32)
+            actP = None
+            an = None
+            if i + 1 < n_down:
+                nx = P["downs"][i + 1]["conv"]
+                an = torch.empty(B, length // 2, C_out, **bf)
+                actP = Act(an, nx["s"], nx["t"], ACT_GELU1702)
+            ops.gemm(ay1, co["W"], pre_shift=co["b"], res=y1, actA=Act(skips[j], un["s"], un["t"], ACT_GELU1702), pool=xn, actP=actP)
+            x, a = xn, an
+            length //= 2
+            self._note(f"downs.{i}.pooled", x)
+        return x, skips
+
+    def _pair_block(self, P, li, single, pair):
+        L = P["layers"][li]
+        sp, pa, pf = L["s2p"], L["pattn"], L["pff"]
+        B, n, D = single.shape
+        dev = single.device
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        pool, H, dp = sp["pool"], sp["heads"], sp["dp"]
+        Pn = n // pool
+        xs = torch.empty(B, Pn, D, **bf)
+        xg = torch.empty(B, Pn, D, **bf)
+        ops.pool_rmsnorm(single, sp["nw"], sp["nb"], xs, xg, pool)
+        qk_plain = torch.empty(B, Pn, 2 * H * dp, **bf)
+        qk_bias = torch.empty(B, Pn, 2 * H * dp, **bf)
+        ops.gemm(xs, sp["Wqk"], actA=Act(qk_plain), actB=Act(qk_bias, None, sp["relbias"]))
+        outer = torch.empty(B, Pn, 2 * dp, **f32)
+        ops.gemm(xg, sp["Wouter"], out=outer)
+        R = self.rel_encoding(li, Pn, dev).view(2 * Pn, H, dp).permute(1, 0, 2)  # [H, 2P, dp] view
+        Np, N2 = _round_up(Pn, 16), _round_up(2 * Pn, 16)
+        qk_out = torch.empty(B, H, Pn, Np, **f32)
+        relq = torch.empty(B, H, Pn, N2, **f32)
+        relk = torch.empty(B, H, Pn, N2, **f32)
+        for b in range(B):
+            qp = qk_plain[b, :, : H * dp].view(Pn, H, dp).permute(1, 0, 2)
+            kp = qk_plain[b, :, H * dp:].view(Pn, H, dp).permute(1, 0, 2)
+            qb = qk_bias[b, :, : H * dp].view(Pn, H, dp).permute(1, 0, 2)
+            kb = qk_bias[b, :, H * dp:].view(Pn, H, dp).permute(1, 0, 2)
+            ops.gemm(qp, kp, w_batched=True, n_pad=Np, out=qk_out[b])       # q_i . k_j            (AG:835)
+            ops.gemm(qb, R, w_batched=True, n_pad=N2, out=relq[b])          # (q_i + bq) . R[p]    (AG:843)
+            ops.gemm(kb, R, w_batched=True, n_pad=N2, out=relk[b])          # (k_j + bk) . R[p]    (AG:844)
+        new_pair = torch.empty(B, Pn, Pn, dp, **f32)
+        ops.pair_combine(qk_out, relq, relk, sp["Wp"], sp["bp"], outer, pair, new_pair, P=Pn)
+        pair = new_pair
+        del qk_out, relq, relk, qk_plain, qk_bias
+        self._note(f"tower.layer{li}.pair_s2p", pair)
+        # --- row attention (AG:1021) ---
+        cells = B * Pn * Pn
+        pn = torch.empty(1, cells, dp, **bf)
+        ops.rmsnorm(pair, pa["nw"], pa["nb"], pn)
+        qkp = torch.empty(1, cells, 2 * dp, **bf)
+        ops.gemm(pn, pa["Wqk"], actA=Act(qkp))
+        vp = torch.empty(1, cells, dp, **bf)
+        ops.gemm(pn, pa["Wv"], actA=Act(vp))
+        Pk = _round_up(Pn, 8)
+        vpt = torch.zeros(B * Pn, dp, Pk, **bf) if Pk != Pn else torch.empty(B * Pn, dp, Pk, **bf)
+        ops.transpose_bf16(vp.view(B * Pn, Pn, dp), vpt)
+        q4 = qkp.view(B, Pn, Pn, 2 * dp)
+        ops.attention(q4[..., :dp], q4[..., dp:], vpt.view(B, Pn, dp, Pk), pair, mode=1, scale=pa["scale"],
+                      out_bias=pa["bv"], res=pair)
+        self._note(f"tower.layer{li}.pair_attn", pair)
+        # --- pair feed-forward (AG:1022) ---
+        ops.rmsnorm(pair, pf["nw"], pf["nb"], pn)
+        hid = torch.empty(1, cells, pf["W1"].shape[1], **bf)
+        ops.gemm(pn, pf["W1"], pre_shift=pf["b1"], relu=True, actA=Act(hid))
+        pflat = pair.view(1, cells, dp)
+        ops.gemm(hid, pf["W2"], pre_shift=pf["b2"], res=pflat, out=pflat)
+        return pair
+
+    def _tower(self, P, x, org_embed, final_act: Act, final_plain: Optional[torch.Tensor]):
+        """x: fp32 [B, n, D] pooled encoder output.  Returns (single fp32, pair fp32)."""
+        B, n, D = x.shape
+        dev = x.device
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        layers = P["layers"]
+        tw = self.unet().transformer
+        if n > tw.max_positions:
+            raise ops._lib.AgbError(f"{n} tokens exceed max_positions={tw.max_positions} (AG:538, 922)")
+        single = torch.empty(B, n, D, **f32)
+        a = torch.empty(B, n, D, **bf)
+        s0, t0 = layers[0]["attn"]["pre"]
+        if org_embed is None:
+            org_embed = torch.zeros(B, D, **f32)
+        ops.add_embed_norm(x, org_embed.to(torch.float32).contiguous(), s0, t0, single, a)
+        cos_t, sin_t = self.rope_tables(n, dev)
+        pair = None
+        a_ff = torch.empty(B, n, D, **bf)
+        for li, L in enumerate(layers):
+            if "s2p" in L:
+                pair = self._pair_block(P, li, single, pair)
+            at = L["attn"]
+            Hh, d, dv = at["heads"], at["d"], at["dv"]
+            qkv = torch.empty(B, n, Hh * d + d + dv, **f32)
+            ops.gemm(a, at["Wqkv"], out=qkv)
+            Q = torch.empty(B, n, Hh * d, **bf)
+            K = torch.empty(B, n, d, **bf)
+            V = torch.empty(B, n, dv, **bf)
+            ops.qkv_post(qkv, Q, K, V, cos_t, sin_t, at["qw"], at["qb"], at["kw"], at["kb"], at["vw"], at["vb"], Hh, d, dv)
+            nk = _round_up(n, 8)
+            Vt = torch.empty(B, dv, nk, **bf)
+            ops.transpose_bf16(V, Vt)
+            Pn = pair.shape[1]
+            bias = torch.empty(B, Hh, Pn, Pn, **f32)
+            ops.pair_bias(pair, at["ab_s"], at["ab_t"], at["ab_W"], bias)
+            O = torch.empty(B, n, Hh * dv, **bf)
+            ops.attention(Q.view(B, n, Hh, d).permute(0, 2, 1, 3), K.view(B, 1, n, d), Vt.view(B, 1, dv, nk),
+                          O.view(B, n, Hh, dv).permute(0, 2, 1, 3), mode=0, scale=at["scale"], bias=bias, softcap=at["softcap"])
+            ff = L["ff"]
+            ops.gemm(O, at["Wout"], pre_scale=at["out_scale"], pre_shift=at["out_shift"], res=single, out=single,
+                     actA=Act(a_ff, ff["pre"][0], ff["pre"][1]))
+            hid = torch.empty(B, n, ff["W1"].shape[1], **bf)
+            ops.gemm(a_ff, ff["W1"], pre_shift=ff["b1"], relu=True, actA=Act(hid))
+            last = li + 1 == len(layers)
+            if not last:
+                nxt = layers[li + 1]["attn"]["pre"]
+                ops.gemm(hid, ff["W2"], pre_scale=ff["out_scale"], pre_shift=ff["out_shift"], res=single, out=single,
+                         actA=Act(a, nxt[0], nxt[1]))
+            else:
+                ops.gemm(hid, ff["W2"], pre_scale=ff["out_scale"], pre_shift=ff["out_shift"], res=single, out=single,
+                         actA=final_act, actB=Act(final_plain) if final_plain is not None else None)
+            self._note(f"tower.layer{li}.single", single)
+            self._note(f"tower.layer{li}.pair", pair)
+        return single, pair
+
+    def _decoder(self, P, x, a, skips, want_plain: bool):
+        B, length, _ = x.shape
+        dev = x.device
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        ups = P["ups"]
+        plain = None
+        for j, u in enumerate(ups):
+            c, un, co = u["conv"], u["unet_conv"], u["conv_out"]
+            C_out = c["W"].shape[1]
+            low = torch.empty(B, length, C_out, **f32)
+            ops.gemm(a, c["W"], pre_shift=c["b"], res=x, res_ch=C_out, post_scale=u["scale"], out=low)
+            y = torch.empty(B, 2 * length, C_out, **f32)
+            ay = torch.empty(B, 2 * length, C_out, **bf)
+            ops.gemm(skips[j], un["W"], pre_shift=un["b"], res=low, res_shift=1, out=y, actA=Act(ay, co["s"], co["t"], ACT_GELU1702))
+            skips[j] = None
+            xn = torch.empty(B, 2 * length, C_out, **f32)
+            if j + 1 < len(ups):
+                nx = ups[j + 1]["conv"]
+                an = torch.empty(B, 2 * length, C_out, **bf)
+                ops.gemm(ay, co["W"], pre_shift=co["b"], res=y, out=xn, actA=Act(an, nx["s"], nx["t"], ACT_GELU1702))
+            else:
+                an = None
+                if want_plain:
+                    plain = torch.empty(B, 2 * length, C_out, **bf)
+                ops.gemm(ay, co["W"], pre_shift=co["b"], res=y, out=xn, actA=Act(plain) if want_plain else None)
+            x, a = xn, an
+            length *= 2
+            self._note(f"ups.{j}", x)
+        return x, plain
+
+    # ------------------------------------------------------------------------------------------ public
+    @torch.no_grad()
+    def run(self, seq, org_embed, organism_index=None, with_embeds=False):
+        if not seq.is_cuda:
+            raise ops._lib.AgbError("alphagenome_b200 has no CPU path: inputs must be CUDA tensors on a B200")
+        seq = seq.to(torch.int64).contiguous()
+        dev = seq.device
+        P = self.pack(dev)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        x, skips = self._encoder(P, seq)
+        B, n, D = x.shape
+        u0 = P["ups"][0]["conv"]
+        a_dec = torch.empty(B, n, D, **bf)
+        single_b16 = torch.empty(B, n, D, **bf) if with_embeds else None
+        single, pair = self._tower(P, x, org_embed, Act(a_dec, u0["s"], u0["t"], ACT_GELU1702), single_b16)
+        unet_out, unet_b16 = self._decoder(P, single, a_dec, skips, want_plain=with_embeds)
+        out = dict(unet_output=unet_out, single_repr=single, pairwise_repr=pair)
+        if with_embeds:
+            f32 = dict(device=dev, dtype=torch.float32)
+            o128, o1, op = P["out128"], P["out1"], P["outpair"]
+            t128 = o128["table"].index_select(0, organism_index)
+            e128 = torch.empty(B, n, o128["W"].shape[1], **f32)
+            e128_b16 = torch.empty(B, n, o128["W"].shape[1], **bf)
+            ops.gemm(single_b16, o128["W"], pre_shift=o128["b"], actA=Act(e128, o128["s"], t128, ACT_GELU1702),
+                     actB=Act(e128_b16, o128["s"], t128, ACT_GELU1702))
+            skp = torch.empty(B, n, o1["Wskip"].shape[1], **f32)
+            ops.gemm(e128_b16, o1["Wskip"], out=skp)
+            Lfull = unet_out.shape[1]
+            shift = int(math.log2(Lfull // n))
+            assert (n << shift) == Lfull
+            t1 = o1["table"].index_select(0, organism_index)
+            e1 = torch.empty(B, Lfull, o1["W"].shape[1], **f32)
+            ops.gemm(unet_b16, o1["W"], pre_shift=o1["b"], res=skp, res_shift=shift, actA=Act(e1, o1["s"], t1, ACT_GELU1702))
+            epair = torch.empty_like(pair)
+            ops.pair_out_embed(pair, op["w"], op["b"], op["emb"].index_select(0, organism_index).contiguous(), epair)
+            out.update(embeds_1bp=e1, embeds_128bp=e128, embeds_pair=epair)
+        return out
+
+    def run_trunk(self, seq, pre_attend_embed=None):
+        return self.run(seq, pre_attend_embed, with_embeds=False)
+
+    def run_embeds(self, seq, organism_index):
+        P = self.pack(seq.device)
+        if "org" not in P:
+            raise ops._lib.AgbError("run_embeds needs the AlphaGenome shell (organism / output embeddings)")
+        organism_index = organism_index.to(seq.device).long()
+        org = P["org"].index_select(0, organism_index)
+        return self.run(seq, org, organism_index=organism_index, with_embeds=True)

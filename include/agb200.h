@@ -85,6 +85,8 @@ typedef struct AgGemmArgs {
   int32_t N;          /* output channels (multiple of 16) */
   int32_t K;          /* input channels (multiple of 8) */
   int32_t taps;       /* 1 or 5 (any odd value <= 15 is accepted) */
+  int32_t w_rows;     /* rows of W present in memory (0 = N); rows in [w_rows, N) read as zero, so N can be padded to 16 */
+  int32_t reserved0;
   const float* pre_scale; /* [N] or NULL */
   const float* pre_shift; /* [N] or NULL (bias, possibly folded with a post-norm) */
   int32_t relu;
@@ -104,6 +106,88 @@ typedef struct AgGemmArgs {
 } AgGemmArgs;
 
 int ag_gemm_fwd(const AgGemmArgs* args, int device, void* stream);
+
+/* ag_attention_fwd: fused attention (QK^T -> softmax -> .V) with tcgen05; replaces the materialised
+ * einsum/softmax/einsum of Attention.forward (AG:748-779; mode 0: + pair bias upsampled x16, tanh soft-cap)
+ * and of PairwiseRowAttention.forward (AG:880-889; mode 1: plain softmax, fp32 out = result + out_bias + res).
+ *   Q  bf16 [batch][heads][n_q][d]      addressed as b*q_bstride + h*q_hstride + i*q_ld + c
+ *   K  bf16 [batch][kv_heads][n_k][d]   (kv_heads == 1: multi-query, shared by all heads)
+ *   Vt bf16 [batch][kv_heads][dv][n_k]  (values TRANSPOSED: keys contiguous; v_ld = elements between dv rows)
+ *   bias fp32 [batch][heads][bias_p][bias_p], bias_p >= n/16     (mode 0 only)
+ *   out [batch][heads][n_q][dv] addressed as b*out_bstride + h*out_hstride + i*out_ld + c; bf16 or fp32
+ */
+typedef struct AgAttnArgs {
+  const void* Q;
+  const void* K;
+  const void* Vt;
+  int64_t q_bstride, q_hstride;
+  int64_t k_bstride, k_hstride;
+  int64_t v_bstride, v_hstride;
+  int32_t q_ld, k_ld, v_ld;
+  int32_t batch, heads, kv_heads, n_q, n_k, d, dv;
+  int32_t mode;       /* 0 = soft-capped + bias (AG:752-765), 1 = plain softmax (AG:880-885) */
+  int32_t bias_p;
+  float scale;        /* d^-0.5 */
+  float softcap;      /* 5.0 (AG:653) */
+  const float* bias;
+  void* out;
+  int64_t out_bstride, out_hstride;
+  int32_t out_ld;
+  int32_t out_dtype;  /* 0 = bf16, 1 = fp32 */
+  const float* out_bias; /* [dv] fp32 or NULL (fp32 out only) */
+  const float* res;      /* fp32, same addressing as out, or NULL (fp32 out only; may alias out) */
+} AgAttnArgs;
+
+int ag_attention_fwd(const AgAttnArgs* args, int device, void* stream);
+
+/* --- vectorised HBM-bound kernels ------------------------------------------------------------------- */
+
+/* tokens int64 [B][L] (A,C,G,T = 0..3; negative = N -> all-zero row, AG:1171-1174) -> bf16 one-hot im2col
+ * [B][L][ld] with column t*n_base + base = 1 iff token[l + t - width/2] == base; columns >= width*n_base are 0.
+ * Feeding this to ag_gemm_fwd with the packed [C][ld] weight is DNAEmbed.conv (AG:1162, 1177). */
+int ag_onehot_im2col_fwd(const int64_t* tokens, void* out_bf16, int32_t B, int32_t L, int32_t width,
+                         int32_t n_base, int32_t ld, int device, void* stream);
+
+/* qkv fp32 [B][n][heads*d + d + dv] -> LayerNorm(eps 1e-5) per head slice, interleaved RoPE on q and k
+ * (AG:715-734, 559-566) -> Q bf16 [B][n][heads*d], K bf16 [B][n][d], V bf16 [B][n][dv].
+ * cos/sin: fp32 [n][d/2] tables of the angles position*inv_freq (AG:545-557). norm_wb: q_w,q_b,k_w,k_b,v_w,v_b. */
+int ag_qkv_post_fwd(const float* qkv, void* Q, void* K, void* V, const float* cos_tab, const float* sin_tab,
+                    const float* q_w, const float* q_b, const float* k_w, const float* k_b, const float* v_w,
+                    const float* v_b, int32_t B, int32_t n, int32_t heads, int32_t d, int32_t dv, int device,
+                    void* stream);
+
+/* bf16 [nb][R][C] (row stride in_ld, batch stride in_bstride) -> bf16 [nb][C][out_ld] with out[b][c][r] = in[b][r][c] */
+int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t C, int64_t in_bstride,
+                      int32_t in_ld, int64_t out_bstride, int32_t out_ld, int device, void* stream);
+
+/* to_attn_bias (AG:688-693): bias[b][g][i][j] = sum_c W[g][c] * gelu_erf(pair[b][i][j][c]*scale[c] + shift[c]) */
+int ag_pair_bias_fwd(const float* pair, const float* scale, const float* shift, const float* W, float* bias,
+                     int32_t B, int32_t P, int32_t C, int32_t heads, int device, void* stream);
+
+/* SingleToPairwise prologue (AG:828-829, 852): mean over `pool` tokens -> RMSNormWithBias ->
+ * x_bf16 [B][P][C] and gelu_erf(x) bf16 [B][P][C] */
+int ag_pool_rmsnorm_fwd(const float* single, const float* w, const float* b, void* x_bf16, void* xg_bf16,
+                        int32_t B, int32_t n, int32_t C, int32_t pool, int device, void* stream);
+
+/* SingleToPairwise combine (AG:835-856): pair[b][i][j][:] = Wp . sim[b][i][j][:] + bp + outer[b][i][:D] +
+ * outer[b][j][D:] (+ prev), with sim[..h] = qk[b][h][i][j] + 0.5*(relq[b][h][i][P+j-i] + relk[b][h][j][P+i-j]);
+ * qk rows are qk_ld floats apart, relq/relk rows rel_ld floats apart (padded to the GEMM's N multiple of 16) */
+int ag_pair_combine_fwd(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
+                        const float* outer, const float* prev, float* pair, int32_t B, int32_t P, int32_t H,
+                        int32_t D, int32_t qk_ld, int32_t rel_ld, int device, void* stream);
+
+/* RMSNormWithBias over the last dim (AG:400-405): fp32 [rows][C] -> bf16 [rows][C] */
+int ag_rmsnorm_fwd(const float* x, const float* w, const float* b, void* out_bf16, int64_t rows, int32_t C,
+                   int device, void* stream);
+
+/* single[b][r][c] = x[b][r][c] + emb[b][c]  (AG:1119-1120);  a_bf16 = single*scale[c] + shift[c] (pre-norm) */
+int ag_add_embed_norm_fwd(const float* x, const float* emb, const float* scale, const float* shift,
+                          float* single, void* a_bf16, int32_t B, int32_t rows, int32_t C, int device,
+                          void* stream);
+
+/* OutputPairEmbedding (AG:1248-1259): out = gelu1702(RMSNormWithBias(0.5*(pair[b][i][j] + pair[b][j][i])) + emb[b]) */
+int ag_pair_out_embed_fwd(const float* pair, const float* w, const float* b, const float* emb, float* out,
+                          int32_t B, int32_t P, int32_t C, int device, void* stream);
 
 /* library / error plumbing */
 int ag_version(void);

@@ -245,6 +245,7 @@ def transformer_unet(sd: SD, seq, organism_embed, p: str = "transformer_unet.", 
     skips = [skip]
     if collect:
         collect("dna_embed.skip", skip)
+        collect("embed.pooled", x)
     n_down = 1 + max(int(k[len(p + "downs."):].split(".")[0]) for k in sd if k.startswith(p + "downs."))
     for i in range(n_down):
         x, skip = down_block(sd, f"{p}downs.{i}.", x)

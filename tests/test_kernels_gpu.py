@@ -1,0 +1,206 @@
+"""-m gpu: every non-GEMM kernel of libagb200 (through the C ABI) against the oracle's function for the same
+step (oracle/trunk_oracle.py, pinned to the reference) or a plain fp32 torch restatement, on seeded inputs.
+
+Tolerances: kernels whose OUTPUT is bf16 are compared at 1.2e-2 of the output scale (bf16 half-ulp is 2^-9
+relative, tanh.approx/ex2.approx add ~2^-11); fp32-output kernels at 2e-3 or tighter."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from alphagenome_b200 import ops
+from oracle import trunk_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_err(got, want):
+    want = want.double().cpu()
+    got = got.double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp(min=1e-6)).item()
+
+
+def g(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,n", [(1, 8, 64), (2, 8, 304), (1, 8, 1024), (1, 2, 16)])
+def test_attention_softcap_bias(B, H, n):
+    d, dv = 128, 192
+    P = n // 16
+    Q = g(B, n, H, d, seed=1).bfloat16()
+    K = g(B, n, d, seed=2).bfloat16()
+    V = g(B, n, dv, seed=3).bfloat16()
+    bias = g(B, H, P, P, seed=4, scale=2.0)
+    scale = d ** -0.5
+    sim = torch.einsum("bihd,bjd->bhij", Q.double(), K.double()) * scale
+    sim = sim + bias.double().repeat_interleave(16, 2).repeat_interleave(16, 3)
+    att = (torch.tanh(sim / 5.0) * 5.0).softmax(-1)
+    want = torch.einsum("bhij,bjd->bihd", att, V.double())
+    nk = (n + 7) // 8 * 8
+    Vt = torch.zeros(B, dv, nk, dtype=torch.bfloat16)
+    Vt[:, :, :n] = V.transpose(1, 2)
+    Qc, Kc, Vtc = Q.to(DEV).contiguous(), K.to(DEV).contiguous(), Vt.to(DEV)
+    out = torch.zeros(B, n, H, dv, dtype=torch.bfloat16, device=DEV)
+    ops.attention(Qc.permute(0, 2, 1, 3), Kc.view(B, 1, n, d), Vtc.view(B, 1, dv, nk), out.permute(0, 2, 1, 3),
+                  mode=0, scale=scale, bias=bias.to(DEV).contiguous(), softcap=5.0)
+    torch.cuda.synchronize()
+    assert rel_err(out, want) < 1.2e-2
+
+
+@pytest.mark.parametrize("B,P", [(1, 4), (2, 24), (1, 136), (1, 1)])
+def test_attention_pair_rows(B, P):
+    D = 128
+    x = g(B, P, P, 2 * D, seed=5, scale=1.5).bfloat16()   # q | k
+    v = g(B, P, P, D, seed=6).bfloat16()
+    bv = g(D, seed=7, scale=0.1)
+    res = g(B, P, P, D, seed=8)
+    q, k = x[..., :D].double(), x[..., D:].double()
+    att = (torch.einsum("bnid,bnjd->bnij", q, k) * D ** -0.5).softmax(-1)
+    want = torch.einsum("bnij,bnjd->bnid", att, v.double()) + bv.double() + res.double()
+    Pk = (P + 7) // 8 * 8
+    vt = torch.zeros(B, P, D, Pk, dtype=torch.bfloat16)
+    vt[..., :P] = v.transpose(2, 3)
+    xc = x.to(DEV).contiguous()
+    pair = res.to(DEV).contiguous()
+    ops.attention(xc[..., :D], xc[..., D:], vt.to(DEV), pair, mode=1, scale=D ** -0.5, out_bias=bv.to(DEV), res=pair)
+    torch.cuda.synchronize()
+    assert rel_err(pair, want) < 1e-2  # P is bf16 (2^-9); outputs fp32
+
+
+# ------------------------------------------------------------------------------------------------ small kernels
+def test_onehot_im2col_matches_conv15():
+    B, L, C = 2, 300, 64
+    seq = torch.from_numpy(np.random.default_rng(0).integers(-1, 4, size=(B, L)))
+    w = g(C, 4, 15, seed=1, scale=0.2)
+    bias = g(C, seed=2, scale=0.1)
+    onehot = F.one_hot(seq.clamp(min=0), 4).float() * (seq >= 0).unsqueeze(-1).float()
+    want = O.conv1d_cl(onehot, w, bias)
+    X = torch.empty(B, L, 64, dtype=torch.bfloat16, device=DEV)
+    ops.onehot_im2col(seq.to(DEV), X, 15, 4)
+    Xc = X.float().cpu()
+    assert set(Xc.unique().tolist()) <= {0.0, 1.0}
+    w2 = torch.zeros(C, 64)
+    w2[:, :60] = w.permute(0, 2, 1).reshape(C, 60)
+    got = Xc @ w2.T + bias
+    assert rel_err(got, want) < 1e-5
+    assert torch.all(Xc[:, :, 60:] == 0)
+
+
+@pytest.mark.parametrize("B,n", [(1, 16), (2, 200)])
+def test_qkv_post_layernorm_rope(B, n):
+    H, d, dv = 8, 128, 192
+    qkv = g(B, n, H * d + d + dv, seed=3, scale=2.0)
+    sd = {f"{k}_norm.{w}": (1 + 0.2 * g(sz, seed=i)) if w == "weight" else 0.1 * g(sz, seed=i + 10)
+          for i, (k, sz) in enumerate((("q", d), ("k", d), ("v", dv))) for w in ("weight", "bias")}
+    ang = O.rotary_table({}, "x.", n)
+    q, k, v = qkv.split((H * d, d, dv), dim=-1)
+    wq = O.apply_rope(ang[None, :, None, :], O.layer_norm(sd, "q_norm.", q.reshape(B, n, H, d))).reshape(B, n, H * d)
+    wk = O.apply_rope(ang[None], O.layer_norm(sd, "k_norm.", k))
+    wv = O.layer_norm(sd, "v_norm.", v)
+    inv = O.rotary_inv_freq(128)
+    a2 = torch.arange(n, dtype=torch.float32)[:, None] * inv[None]
+    Q = torch.empty(B, n, H * d, dtype=torch.bfloat16, device=DEV)
+    K = torch.empty(B, n, d, dtype=torch.bfloat16, device=DEV)
+    V = torch.empty(B, n, dv, dtype=torch.bfloat16, device=DEV)
+    c = lambda t: t.to(DEV).contiguous()
+    ops.qkv_post(c(qkv), Q, K, V, c(a2.cos()), c(a2.sin()), c(sd["q_norm.weight"]), c(sd["q_norm.bias"]), c(sd["k_norm.weight"]),
+                 c(sd["k_norm.bias"]), c(sd["v_norm.weight"]), c(sd["v_norm.bias"]), H, d, dv)
+    for got, want in ((Q, wq), (K, wk), (V, wv)):
+        assert rel_err(got, want) < 6e-3
+
+
+def test_transpose_bf16():
+    x = g(3, 70, 130, seed=1).bfloat16().to(DEV)
+    out = torch.zeros(3, 130, 72, dtype=torch.bfloat16, device=DEV)
+    ops.transpose_bf16(x, out)
+    assert torch.equal(out[:, :, :70], x.transpose(1, 2))
+    assert torch.all(out[:, :, 70:] == 0)
+
+
+def test_pair_bias_projection():
+    B, P = 2, 9
+    pair = g(B, P, P, 128, seed=2, scale=3.0)
+    sd = {"to_attn_bias.0.gamma": 1 + 0.2 * g(128, seed=3), "to_attn_bias.0.beta": 0.1 * g(128, seed=4),
+          "to_attn_bias.0.running_var": torch.rand(128) + 0.5, "to_attn_bias.2.weight": g(8, 128, seed=5, scale=0.1)}
+    want = O.attention_bias(sd, "", pair)
+    s, t = O.batch_rms_affine(sd, "to_attn_bias.0.")
+    out = torch.empty(B, 8, P, P, device=DEV)
+    c = lambda t: t.to(DEV).contiguous()
+    ops.pair_bias(c(pair), c(s), c(t), c(sd["to_attn_bias.2.weight"]), out)
+    assert rel_err(out, want) < 1e-5
+
+
+def test_pool_rmsnorm():
+    B, n, C = 2, 64, 1536
+    single = g(B, n, C, seed=6, scale=2.0)
+    sd = {"norm.weight": 1 + 0.2 * g(C, seed=7), "norm.bias": 0.1 * g(C, seed=8)}
+    want = O.rms_norm_bias(sd, "norm.", single.reshape(B, n // 16, 16, C).mean(2))
+    x = torch.empty(B, n // 16, C, dtype=torch.bfloat16, device=DEV)
+    xg = torch.empty_like(x)
+    c = lambda t: t.to(DEV).contiguous()
+    ops.pool_rmsnorm(c(single), c(sd["norm.weight"]), c(sd["norm.bias"]), x, xg, 16)
+    assert rel_err(x, want) < 6e-3
+    assert rel_err(xg, F.gelu(want)) < 6e-3
+
+
+@pytest.mark.parametrize("P", [4, 37])
+def test_pair_combine(P):
+    B, H, D = 2, 32, 128
+    Np, N2 = (P + 15) // 16 * 16, (2 * P + 15) // 16 * 16
+    qk = g(B, H, P, Np, seed=1)
+    relq = g(B, H, P, N2, seed=2)
+    relk = g(B, H, P, N2, seed=3)
+    Wp, bp = g(D, H, seed=4, scale=0.2), g(D, seed=5, scale=0.1)
+    outer = g(B, P, 2 * D, seed=6)
+    prev = g(B, P, P, D, seed=7)
+    i = torch.arange(P)
+    col = P + (i[None, :] - i[:, None])
+    rq = relq[..., : 2 * P].gather(3, col[None, None].expand(B, H, P, P))
+    rk = relk[..., : 2 * P].gather(3, col[None, None].expand(B, H, P, P))
+    sim = qk[..., :P].permute(0, 2, 3, 1) + 0.5 * (rq.permute(0, 2, 3, 1) + rk.permute(0, 3, 2, 1))
+    want = sim @ Wp.T + bp + outer[:, :, None, :D] + outer[:, None, :, D:] + prev
+    out = torch.empty(B, P, P, D, device=DEV)
+    c = lambda t: t.to(DEV).contiguous()
+    ops.pair_combine(c(qk), c(relq), c(relk), c(Wp), c(bp), c(outer), c(prev), out, P=P)
+    assert rel_err(out, want) < 1e-5
+    ops.pair_combine(c(qk), c(relq), c(relk), c(Wp), c(bp), c(outer), None, out, P=P)
+    assert rel_err(out, want - prev) < 1e-5
+
+
+def test_rmsnorm_rows():
+    x = g(1000, 128, seed=9, scale=4.0)
+    sd = {"n.weight": 1 + 0.2 * g(128, seed=1), "n.bias": 0.1 * g(128, seed=2)}
+    out = torch.empty(1000, 128, dtype=torch.bfloat16, device=DEV)
+    c = lambda t: t.to(DEV).contiguous()
+    ops.rmsnorm(c(x), c(sd["n.weight"]), c(sd["n.bias"]), out)
+    assert rel_err(out, O.rms_norm_bias(sd, "n.", x)) < 6e-3
+
+
+def test_add_embed_norm():
+    B, n, C = 2, 48, 1536
+    x, emb = g(B, n, C, seed=3), g(B, C, seed=4)
+    s, t = 1 + 0.2 * g(C, seed=5), 0.1 * g(C, seed=6)
+    single = torch.empty(B, n, C, device=DEV)
+    a = torch.empty(B, n, C, dtype=torch.bfloat16, device=DEV)
+    c = lambda t: t.to(DEV).contiguous()
+    ops.add_embed_norm(c(x), c(emb), c(s), c(t), single, a)
+    want = x + emb[:, None]
+    assert rel_err(single, want) < 1e-6
+    assert rel_err(a, want * s + t) < 6e-3
+
+
+def test_pair_out_embed():
+    B, P = 2, 11
+    pair = g(B, P, P, 128, seed=7, scale=3.0)
+    sd = {"p.norm.weight": 1 + 0.2 * g(128, seed=8), "p.norm.bias": 0.1 * g(128, seed=9), "p.embed.weight": g(2, 128, seed=10)}
+    org = torch.tensor([1, 0])
+    want = O.output_pair_embedding(sd, "p.", pair, org)
+    out = torch.empty(B, P, P, 128, device=DEV)
+    c = lambda t: t.to(DEV).contiguous()
+    ops.pair_out_embed(c(pair), c(sd["p.norm.weight"]), c(sd["p.norm.bias"]), c(sd["p.embed.weight"][org]), out)
+    assert rel_err(out, want) < 1e-5

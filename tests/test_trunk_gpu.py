@@ -1,0 +1,102 @@
+"""-m gpu: the whole B200 trunk forward (AlphaGenome(dna, organism_index) -> Embeds, through the C ABI)
+against (1) golden outputs of the unmodified reference (tests/golden/*.npz) and (2) the pinned CPU oracle,
+stage by stage.  Tolerance (BASELINE.json north_star): max|d| / max|ref| <= 1e-2 on the three embeddings."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from alphagenome_b200.init_weights import apply_synth_weights
+from alphagenome_b200.model import AlphaGenome
+from alphagenome_b200.trunk import engine_for
+from oracle import trunk_oracle as O
+from tests.golden_util import CASES, make_inputs, sample_rows
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+OUTPUTS = ["embeds_1bp", "embeds_128bp", "embeds_pair", "unet_output", "single_repr", "pairwise_repr"]
+TOL = 1e-2
+
+_MODEL = {}
+
+
+def model_with_seed(seed):
+    if "m" not in _MODEL:
+        _MODEL["m"] = AlphaGenome().cuda().eval()
+    apply_synth_weights(_MODEL["m"], seed=seed)
+    return _MODEL["m"]
+
+
+def pearson(a, b):
+    a = a.double().flatten() - a.double().mean()
+    b = b.double().flatten() - b.double().mean()
+    return float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_trunk_matches_reference_golden(case):
+    g = np.load(GOLD / f"{case['name']}.npz")
+    seq, org = make_inputs(case)
+    m = model_with_seed(case["weight_seed"])
+    emb, tu = m.get_embeds(seq.cuda(), org.cuda(), return_unet_transformer_outputs=True)
+    torch.cuda.synchronize()
+    got = dict(zip(OUTPUTS, list(emb) + list(tu)))
+    report = {}
+    for name in OUTPUTS:
+        t = got[name].float().cpu()
+        idx = sample_rows(name, t.shape)
+        t = t if idx is None else t[:, idx]
+        want = torch.from_numpy(g[name])
+        err = (t - want).abs().max().item() / float(g[name + "__absmax"])
+        report[name] = (err, pearson(t, want) if want.numel() > 128 else 1.0)
+    bad = {k: v for k, v in report.items() if not (v[0] <= TOL and v[1] >= 0.999)}
+    assert not bad, report
+
+
+def test_trunk_stagewise_vs_oracle():
+    """Per-stage parity on B=2, L=8192 (BASELINE config 2) with N tokens and both organisms."""
+    case = CASES[1]
+    seq, org = make_inputs(case)
+    m = model_with_seed(case["weight_seed"])
+    sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+    ref = {}
+    O.alphagenome_embeds(sd, seq, org, collect=lambda k, v: ref.__setitem__(k, v.clone()))
+    mine = {}
+    eng = engine_for(m.transformer_unet, m)
+    eng.collect = lambda k, v: mine.__setitem__(k, v.detach().float().cpu().clone())
+    try:
+        m.get_embeds(seq.cuda(), org.cuda())
+        torch.cuda.synchronize()
+    finally:
+        eng.collect = None
+    common = [k for k in mine if k in ref and ref[k] is not None]
+    assert len(common) >= 20, sorted(mine)
+    report = {k: ((mine[k] - ref[k]).abs().max() / ref[k].abs().max()).item() for k in common}
+    bad = {k: v for k, v in report.items() if not v <= TOL}
+    assert not bad, report
+
+
+def test_determinism_and_batch_independence():
+    """Reference tests/test_integration_jax_torch.py:468-517: same input twice -> identical; a sample's output
+    does not depend on its batch neighbours."""
+    m = model_with_seed(0)
+    seq = torch.from_numpy(np.random.default_rng(3).integers(0, 4, size=(2, 4096))).cuda()
+    org = torch.tensor([0, 1]).cuda()
+    a = m.get_embeds(seq, org)
+    b = m.get_embeds(seq, org)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    c = m.get_embeds(seq[1:], org[1:])
+    for x, y in zip(a, c):
+        assert torch.allclose(x[1:], y, rtol=1e-3, atol=1e-3 * float(y.abs().max()))
+
+
+def test_rejects_cpu_tensors_and_bad_length():
+    from alphagenome_b200._lib import AgbError
+
+    m = model_with_seed(0)
+    with pytest.raises(AgbError):
+        m.get_embeds(torch.zeros(1, 2048, dtype=torch.long), 0)
+    with pytest.raises(AgbError):
+        m.get_embeds(torch.zeros(1, 2048 + 128, dtype=torch.long).cuda(), 0)
