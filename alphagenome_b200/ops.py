@@ -15,6 +15,10 @@ from . import _lib
 from ._lib import ACT_GELU1702, ACT_GELU_ERF, ACT_NONE, ACT_RELU, AgAttnArgs, AgEpiOut, AgGemmArgs  # noqa: F401
 
 
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per ag_gemm_fwd launch
+PROFILE_GEMM = None
+
+
 @dataclass
 class Act:
     """One fused activated output: dst = act(v * scale + shift)."""
@@ -116,13 +120,13 @@ def gemm(
 
     g = AgGemmArgs()
     g.A = A.data_ptr()
-    g.a_bstride = A.stride(0)
+    g.a_bstride = A.stride(0) if batch > 1 else A.stride(1) * a_rows  # stride of a size-1 dim is arbitrary
     g.a_ld = A.stride(1)
     g.a_rows = a_rows
     g.a_row0 = a_row0
     g.w_batched = 1 if w_batched else 0
     g.W = W.data_ptr()
-    g.w_zstride = W.stride(0)
+    g.w_zstride = W.stride(0) if W.shape[0] > 1 else W.stride(1) * W.shape[1]
     g.w_ld = W.stride(1)
     g.batch, g.M, g.N, g.K, g.taps = batch, M, N, K, taps
     g.w_rows = w_rows
@@ -165,6 +169,13 @@ def gemm(
     _fill_act(g.actA, actA, batch, M, N)
     _fill_act(g.actB, actB, batch, M, N)
     _fill_act(g.actP, actP, batch, M // 2, N)
+    if PROFILE_GEMM is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
+        e1.record()
+        PROFILE_GEMM.append((e0, e1, 2.0 * batch * M * (w_rows or N) * K * taps))
+        return
     _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
 
 
@@ -202,9 +213,12 @@ def attention(
     _require(out.dim() == 4 and tuple(out.shape) == (B, H, n_q, dv) and out.stride(3) == 1, f"out must be [B,H,n_q,dv], got {tuple(out.shape)}")
     a = AgAttnArgs()
     a.Q, a.K, a.Vt = Q.data_ptr(), K.data_ptr(), Vt.data_ptr()
-    a.q_bstride, a.q_hstride, a.q_ld = Q.stride(0), Q.stride(1), Q.stride(2)
-    a.k_bstride, a.k_hstride, a.k_ld = K.stride(0), K.stride(1), K.stride(2)
-    a.v_bstride, a.v_hstride, a.v_ld = Vt.stride(0), Vt.stride(1), Vt.stride(2)
+    def st(t, i):  # the stride of a size-1 dim is arbitrary: give TMA a well-formed one
+        return t.stride(i) if t.shape[i] > 1 else max(t.stride(j) * t.shape[j] for j in range(i + 1, 4))
+
+    a.q_bstride, a.q_hstride, a.q_ld = st(Q, 0), st(Q, 1), Q.stride(2)
+    a.k_bstride, a.k_hstride, a.k_ld = st(K, 0), st(K, 1), K.stride(2)
+    a.v_bstride, a.v_hstride, a.v_ld = st(Vt, 0), st(Vt, 1), Vt.stride(2)
     a.batch, a.heads, a.kv_heads, a.n_q, a.n_k, a.d, a.dv = B, H, Hk, n_q, n_k, d, dv
     a.mode = mode
     a.scale, a.softcap = float(scale), float(softcap)
@@ -213,7 +227,7 @@ def attention(
         _require(bias.dim() == 4 and bias.shape[0] == B and bias.shape[1] == H and bias.shape[2] == bias.shape[3], "bias must be [B,H,P,P]")
         a.bias, a.bias_p = bias.data_ptr(), bias.shape[2]
     a.out = out.data_ptr()
-    a.out_bstride, a.out_hstride, a.out_ld = out.stride(0), out.stride(1), out.stride(2)
+    a.out_bstride, a.out_hstride, a.out_ld = st(out, 0), st(out, 1), out.stride(2)
     a.out_dtype = 0 if out.dtype == torch.bfloat16 else 1
     _f32(out_bias, "out_bias")
     a.out_bias = _ptr(out_bias)

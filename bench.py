@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 AlphaGenome trunk forward (BASELINE.json metric: trunk forward bp/s at 1 Mbp context).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--length L] [--impl reference]
+
+A "step" is one trunk forward  AlphaGenome(dna, organism_index) -> Embeds  over one batch of synthetic DNA
+tokens (uniform A/C/G/T, np.random.default_rng(42)) with synthetic weights of the published architecture.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "trunk_forward_bp_per_s"
+UNIT = "bp/s"
+FULL_L = 1_048_576
+CPU_SAMPLE_L = 131_072
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def synth_tokens(B, L):
+    return torch.from_numpy(np.random.default_rng(42).integers(0, 4, size=(B, L)).astype(np.int64))
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arms
+def cpu_oracle_bps(L, threads, repeats=1, warmup=0):
+    """The pinned CPU oracle (a port of the reference forward, see oracle/trunk_oracle.py) on the host cores."""
+    from alphagenome_b200.init_weights import synth_state_dict
+    from alphagenome_b200.model import AlphaGenome
+    from oracle import trunk_oracle as O
+
+    torch.set_num_threads(threads)
+    m = AlphaGenome()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.is_floating_point()}
+    sd = {k: v for k, v in m.state_dict().items()}
+    sd.update(synth_state_dict(shapes, seed=0))
+    del m
+    seq = synth_tokens(1, L)
+    org = torch.zeros(1, dtype=torch.long)
+    times = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        O.alphagenome_embeds(sd, seq, org)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return L / float(np.median(times)), float(np.median(times))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    bps, secs = cpu_oracle_bps(CPU_SAMPLE_L, cores, repeats=args.steps, warmup=min(args.warmup, 1))
+    sample = f"B=1 x {CPU_SAMPLE_L} bp window (1/8 of the 1 Mbp workload), fp32, {cores} threads"
+    line = dict(metric=METRIC, value=bps, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=secs * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=workload_config(args.length, args.gpus),
+                cpu_baseline=dict(value=bps, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=bps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(L, gpus):
+    return dict(workload=f"AlphaGenome() trunk forward (conv encoder + 9-layer tower with pair blocks + conv decoder + output embeddings), "
+                         f"B=1 x {L} bp per GPU, synthetic weights (default 7-stage dims 768..1536), no heads",
+                length_bp=L, batch_per_gpu=1, parallelism=f"dp{gpus} (independent sequence per GPU, no data-path collective)",
+                l2="per-step inputs+activations >> 126 MB L2 (1bp activations are GBs); no explicit flush needed")
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--length", type=int, default=FULL_L)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from alphagenome_b200 import _lib, ops
+    from alphagenome_b200.init_weights import apply_synth_weights
+    from alphagenome_b200.model import AlphaGenome
+
+    _lib.check(_lib.load().ag_check_device(local_rank))
+    model = AlphaGenome().to(dev).eval()
+    apply_synth_weights(model, seed=0)
+    L, B = args.length, 1
+    tok_host = synth_tokens(B, L).pin_memory()
+    org_host = torch.zeros(B, dtype=torch.long).pin_memory()
+    tok_dev = tok_host.to(dev)
+    org_dev = org_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return model(tok_dev, org_dev)
+
+    def step_e2e():
+        t = tok_host.to(dev, non_blocking=True)
+        o = org_host.to(dev, non_blocking=True)
+        emb = model(t, o)
+        # result read-back: the whole 128 bp embedding and the pair embedding (the 1 bp embedding stays on the
+        # device for downstream heads, as in the reference's get_embeds -> heads flow)
+        return emb.embeds_128bp.to("cpu", non_blocking=False), emb.embeds_pair.to("cpu", non_blocking=False)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # --- timed: device-resident inputs ---
+    ops.PROFILE_GEMM = []
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = ops.PROFILE_GEMM
+    ops.PROFILE_GEMM = None
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    gemm_flops = sum(f for _, _, f in prof)
+    n_gemm = len(prof)
+
+    # --- timed: end to end through the public API with host buffers ---
+    out = step_e2e()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        out = step_e2e()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1) / args.steps
+    h2d = tok_host.numel() * 8 + org_host.numel() * 8
+    d2h = sum(t.numel() * t.element_size() for t in out)
+
+    tms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = tms.tolist()
+    if rank != 0:
+        return
+    pk = peaks()
+    value = world * B * L / (ms * 1e-3)
+    e2e = world * B * L / (ms_e2e * 1e-3)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 operands / fp32 accumulate + fp32 residual stream",
+                data="synthetic", config=workload_config(L, world),
+                e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                gpu_launches=int(launches), clocks=clocks,
+                roofline=dict(kernel="gemm_conv_kernel (tcgen05 implicit-GEMM conv/linear)", bound="tensor", achieved=achieved,
+                              peak=pk["tf_sustained"], unit="TFLOP/s", frac=(achieved / pk["tf_sustained"]) if achieved else None,
+                              traffic=None, peak_source=pk["src"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
+                              launches_per_step=n_gemm // max(args.steps, 1), share_of_step=gemm_ms / (ms * args.steps),
+                              algorithmic_tflop_per_step=gemm_flops / max(args.steps, 1) / 1e12))
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        bps, secs = cpu_oracle_bps(CPU_SAMPLE_L, cores)
+        line["cpu_baseline"] = dict(value=bps, unit=UNIT, cores=cores, kind="port", seconds=secs,
+                                    sample=f"one forward of B=1 x {CPU_SAMPLE_L} bp (1/8 of the workload) through the pinned CPU oracle, fp32")
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
