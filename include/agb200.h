@@ -196,6 +196,9 @@ const char* ag_last_error(void);
 uint64_t ag_launch_count(void);
 /* 0 if `device` is an sm_100 part and the kernels can be loaded, else non-zero with ag_last_error() */
 int ag_check_device(int device);
+/* device watchdog: a kernel whose mbarrier wait exceeds ~4 s records {0xDEAD0000|tag, blockIdx, threadIdx, parity}
+ * in host-mapped memory and traps (never hangs the GPU); returns non-zero if such a record exists. */
+int ag_watchdog_status(int device, uint32_t out[4]);
 
 #ifdef __cplusplus
 }

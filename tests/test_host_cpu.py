@@ -1,0 +1,77 @@
+"""CPU: host-side logic that needs no GPU — the C-ABI library loads and exports every declared symbol, the host
+model mirrors the reference's parameter contract, the weight generator is deterministic, the header and the
+ctypes mirror agree on struct sizes, and the product path refuses to run without CUDA."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from alphagenome_b200 import _lib
+from alphagenome_b200.init_weights import synth_state_dict, synth_tensor
+from alphagenome_b200.model import AlphaGenome, Embeds, publication_heads_config
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from alphagenome_b200.csrc.build import build
+
+    build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = (ROOT / "include" / "agb200.h").read_text()
+    declared = set(re.findall(r"\b(ag_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared <= set(_lib.EXPORTED), declared - set(_lib.EXPORTED)
+    for name in declared | set(_lib.EXPORTED):
+        assert hasattr(lib, name), f"libagb200.so does not export {name}"
+    assert lib.ag_version() == 1
+    assert lib.ag_launch_count() == 0  # nothing launched on a CPU-only box
+
+
+def test_struct_layout_matches_header(lib, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "agb200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(AgEpiOut), sizeof(AgGemmArgs), sizeof(AgAttnArgs));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.AgEpiOut), C.sizeof(_lib.AgGemmArgs), C.sizeof(_lib.AgAttnArgs)]
+
+
+def test_no_gpu_is_a_loud_error(lib):
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    assert lib.ag_check_device(0) != 0
+    assert _lib.last_error()
+    m = AlphaGenome(dims=(128, 256), transformer_kwargs=dict(depth=1))
+    with pytest.raises(_lib.AgbError):
+        m(torch.zeros(1, 2048, dtype=torch.long), 0)
+
+
+def test_state_dict_contract_matches_reference():
+    ref = {}
+    for line in (ROOT / "tests" / "golden" / "state_dict_keys.txt").read_text().splitlines():
+        k, shp = re.match(r"(\S+) \((.*)\)", line).groups()
+        ref[k] = tuple(int(x) for x in shp.replace(",", " ").split())
+    mine = {k: tuple(v.shape) for k, v in AlphaGenome().state_dict().items()}
+    assert mine == ref
+    assert Embeds._fields == ("embeds_1bp", "embeds_128bp", "embeds_pair")
+    assert publication_heads_config["human"]["num_tracks_1bp"] == 3165
+
+
+def test_synthetic_weights_are_deterministic_and_perturbed():
+    a = synth_tensor(0, "transformer_unet.downs.0.conv.net.0.running_var", (896,))
+    b = synth_tensor(0, "transformer_unet.downs.0.conv.net.0.running_var", (896,))
+    c = synth_tensor(1, "transformer_unet.downs.0.conv.net.0.running_var", (896,))
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert a.min() >= 0.5 and a.max() <= 1.5
+    sd = synth_state_dict({"x.gamma": (8,), "x.beta": (8,), "y.weight": (4, 16), "rotary_emb.inv_freq": (64,)})
+    assert "rotary_emb.inv_freq" not in sd  # formula buffer, never randomised
+    assert abs(float(sd["x.gamma"].mean()) - 1) < 0.2 and float(sd["y.weight"].abs().max()) <= 0.25
