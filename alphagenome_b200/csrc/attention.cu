@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     const float sc_exp = a.softcap * LOG2E;              // exp(softcap * tanh(.))
     const float sc_plain = a.scale * LOG2E;
     const int brow = (row < a.n_q ? row : a.n_q - 1) / 16;
-    const float* bias_row = a.mode == 0 ? a.bias + (((long)b * a.heads + h) * a.bias_p + brow) * a.bias_p : nullptr;
+    const int brows = a.bias_rows > 0 ? a.bias_rows : a.bias_p;
+    const float* bias_row = a.mode == 0 ? a.bias + (((long)b * a.heads + h) * brows + brow) * a.bias_p : nullptr;
     uint8_t* prow = sP + lrow * 128;          // this row inside a swizzle atom-column
     const int sw = lrow & 7;
 
@@ -341,7 +342,8 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
   if (a.mode != 0 && a.mode != 1) return set_error("ag_attention_fwd: mode must be 0 (softcap+bias) or 1 (plain softmax)");
   if (a.mode == 0) {
     if (!a.bias || a.softcap <= 0.f) return set_error("ag_attention_fwd: mode 0 needs bias and softcap > 0");
-    if (a.bias_p * 16 < a.n_k || a.bias_p * 16 < a.n_q) return set_error("ag_attention_fwd: bias [P=%d] must cover n/16 rows and cols", a.bias_p);
+    const int brows = a.bias_rows > 0 ? a.bias_rows : a.bias_p;
+    if (a.bias_p * 16 < a.n_k || brows * 16 < a.n_q) return set_error("ag_attention_fwd: bias [%d x %d] must cover n_q/16 rows and n_k/16 cols", brows, a.bias_p);
   }
   if (a.out_dtype != 0 && a.out_dtype != 1) return set_error("ag_attention_fwd: bad out_dtype");
   if ((a.q_ld | a.k_ld | a.v_ld) % 8 || (a.q_hstride | a.k_hstride | a.v_hstride | a.q_bstride | a.k_bstride | a.v_bstride) % 8)

@@ -145,9 +145,10 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv
 // ---------------------------------------------------------------------------------------------------
 __global__ void pair_bias_kernel(const float* __restrict__ pair, const float* __restrict__ scale,
                                  const float* __restrict__ shift, const float* __restrict__ W, float* __restrict__ bias,
-                                 int B, int P, int heads) {
+                                 int B, int rows, int cols, int heads) {
   const int lane = threadIdx.x & 31;
-  const long cells = (long)B * P * P;
+  const long per_b = (long)rows * cols;
+  const long cells = (long)B * per_b;
   const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + lane);
   const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + lane);
   for (long cell = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; cell < cells;
@@ -157,13 +158,13 @@ __global__ void pair_bias_kernel(const float* __restrict__ pair, const float* __
     x.y = act_apply(fmaf(x.y, sc.y, sh.y), ACT_GELU_ERF);
     x.z = act_apply(fmaf(x.z, sc.z, sh.z), ACT_GELU_ERF);
     x.w = act_apply(fmaf(x.w, sc.w, sh.w), ACT_GELU_ERF);
-    const long b = cell / ((long)P * P);
-    const long ij = cell - b * (long)P * P;
+    const long b = cell / per_b;
+    const long ij = cell - b * per_b;
     for (int g = 0; g < heads; ++g) {
       const float4 w = __ldg(reinterpret_cast<const float4*>(W + g * 128) + lane);
       float d = x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w;
       d = warp_sum(d);
-      if (lane == 0) bias[(b * heads + g) * (long)P * P + ij] = d;
+      if (lane == 0) bias[(b * heads + g) * per_b + ij] = d;
     }
   }
 }
@@ -210,9 +211,11 @@ __global__ void pair_combine_kernel(const float* __restrict__ qk, const float* _
                                     const float* __restrict__ relk, const float* __restrict__ Wp,
                                     const float* __restrict__ bp, const float* __restrict__ outer,
                                     const float* __restrict__ prev, float* __restrict__ pair, int P, int H, int D, int qk_ld,
-                                    int rel_ld) {
+                                    int rel_ld, int rows, int i_off) {
+  // il = local row (this rank owns rows [i_off, i_off + rows) of the P x P pair tensor); i = global row
   extern __shared__ float sim_s[];  // [32][H + 1]
-  const int jt = blockIdx.x, i = blockIdx.y, b = blockIdx.z;
+  const int jt = blockIdx.x, il = blockIdx.y, b = blockIdx.z;
+  const int i = il + i_off;
   const int j0 = jt * 32;
   const int HS = H + 1;
   for (int idx = threadIdx.x; idx < 32 * H; idx += blockDim.x) {
@@ -221,8 +224,8 @@ __global__ void pair_combine_kernel(const float* __restrict__ qk, const float* _
     float s = 0.f;
     if (j < P) {
       const long bh = (long)b * H + h;
-      s = qk[(bh * P + i) * qk_ld + j] +
-          0.5f * (relq[(bh * P + i) * (long)rel_ld + (P + j - i)] + relk[(bh * P + j) * (long)rel_ld + (P + i - j)]);
+      s = qk[(bh * rows + il) * qk_ld + j] +
+          0.5f * (relq[(bh * rows + il) * (long)rel_ld + (P + j - i)] + relk[(bh * P + j) * (long)rel_ld + (P + i - j)]);
     }
     sim_s[jj * HS + h] = s;
   }
@@ -238,7 +241,7 @@ __global__ void pair_combine_kernel(const float* __restrict__ qk, const float* _
       float acc = base + outer[((long)b * P + j) * (2 * D) + D + c];
 #pragma unroll
       for (int h = 0; h < 32; ++h) acc = fmaf(wrow[h], sim_s[jj * HS + h], acc);
-      const long o = (((long)b * P + i) * P + j) * D + c;
+      const long o = (((long)b * rows + il) * P + j) * D + c;
       if (prev) acc += prev[o];
       pair[o] = acc;
     }
@@ -299,20 +302,23 @@ __global__ void add_embed_norm_kernel(const float4* __restrict__ x, const float*
 // ---------------------------------------------------------------------------------------------------
 // OutputPairEmbedding (AG:1248-1259; symmetrize AG:121-122).  One warp per cell, C = 128.
 // ---------------------------------------------------------------------------------------------------
-__global__ void pair_out_embed_kernel(const float* __restrict__ pair, const float* __restrict__ w,
-                                      const float* __restrict__ bvec, const float* __restrict__ emb,
-                                      float* __restrict__ out, int B, int P) {
+__global__ void pair_out_embed_kernel(const float* __restrict__ pair, const float* __restrict__ pairT,
+                                      const float* __restrict__ w, const float* __restrict__ bvec,
+                                      const float* __restrict__ emb, float* __restrict__ out, int B, int rows, int P) {
+  // pair: this rank's rows [B][rows][P][128].  pairT: the transposed blocks, [P/rows][B][rows (j)][rows (i)][128]
+  // (block s holds pair[b][s*rows + jl][i_off + il]); with one rank rows == P and pairT == pair.
   const int lane = threadIdx.x & 31;
-  const long cells = (long)B * P * P;
+  const long cells = (long)B * rows * P;
   const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + lane);
   const float4 bb = __ldg(reinterpret_cast<const float4*>(bvec) + lane);
   for (long cell = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; cell < cells;
        cell += ((long)gridDim.x * blockDim.x) >> 5) {
-    const long b = cell / ((long)P * P);
-    const long ij = cell - b * (long)P * P;
-    const long i = ij / P, j = ij - i * P;
+    const long b = cell / ((long)rows * P);
+    const long ij = cell - b * (long)rows * P;
+    const long il = ij / P, j = ij - il * P;
+    const long sblk = j / rows, jl = j - sblk * rows;
     const float4 a = __ldg(reinterpret_cast<const float4*>(pair + cell * 128) + lane);
-    const float4 t = __ldg(reinterpret_cast<const float4*>(pair + ((b * P + j) * P + i) * 128) + lane);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(pairT + (((sblk * B + b) * rows + jl) * rows + il) * 128) + lane);
     float4 v;
     v.x = 0.5f * (a.x + t.x); v.y = 0.5f * (a.y + t.y); v.z = 0.5f * (a.z + t.z); v.w = 0.5f * (a.w + t.w);
     const float inv = rsqrtf(warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) / 128.0f + 1e-5f);
@@ -361,10 +367,10 @@ int launch_transpose_bf16(const void* in, void* out, int nb, int R, int C, long 
 }
 
 int launch_pair_bias(const float* pair, const float* scale, const float* shift, const float* W, float* bias, int B,
-                     int P, int C, int heads, int device, cudaStream_t st) {
+                     int rows, int cols, int C, int heads, int device, cudaStream_t st) {
   if (C != 128) return set_error("ag_pair_bias_fwd: built for pair dim 128 (got %d)", C);
-  const long cells = (long)B * P * P;
-  pair_bias_kernel<<<grid_for(cells * 32, 256, device), 256, 0, st>>>(pair, scale, shift, W, bias, B, P, heads);
+  const long cells = (long)B * rows * cols;
+  pair_bias_kernel<<<grid_for(cells * 32, 256, device), 256, 0, st>>>(pair, scale, shift, W, bias, B, rows, cols, heads);
   return check_launch("ag_pair_bias_fwd");
 }
 
@@ -378,11 +384,12 @@ int launch_pool_rmsnorm(const float* single, const float* w, const float* b, voi
 
 int launch_pair_combine(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
                         const float* outer, const float* prev, float* pair, int B, int P, int H, int D, int qk_ld,
-                        int rel_ld, int device, cudaStream_t st) {
+                        int rel_ld, int rows, int i_off, int device, cudaStream_t st) {
   if (H != 32) return set_error("ag_pair_combine_fwd: built for 32 pair heads (got %d)", H);
   if (qk_ld < P || rel_ld < 2 * P) return set_error("ag_pair_combine_fwd: qk_ld/rel_ld too small");
-  dim3 grid((P + 31) / 32, P, B);
-  pair_combine_kernel<<<grid, 128, 32 * (H + 1) * sizeof(float), st>>>(qk, relq, relk, Wp, bp, outer, prev, pair, P, H, D, qk_ld, rel_ld);
+  if (rows < 1 || i_off < 0 || i_off + rows > P) return set_error("ag_pair_combine_fwd: row range [%d, %d) outside P=%d", i_off, i_off + rows, P);
+  dim3 grid((P + 31) / 32, rows, B);
+  pair_combine_kernel<<<grid, 128, 32 * (H + 1) * sizeof(float), st>>>(qk, relq, relk, Wp, bp, outer, prev, pair, P, H, D, qk_ld, rel_ld, rows, i_off);
   return check_launch("ag_pair_combine_fwd");
 }
 
@@ -402,11 +409,12 @@ int launch_add_embed_norm(const float* x, const float* emb, const float* scale, 
   return check_launch("ag_add_embed_norm_fwd");
 }
 
-int launch_pair_out_embed(const float* pair, const float* w, const float* b, const float* emb, float* out, int B, int P,
-                          int C, int device, cudaStream_t st) {
+int launch_pair_out_embed(const float* pair, const float* pairT, const float* w, const float* b, const float* emb,
+                          float* out, int B, int rows, int P, int C, int device, cudaStream_t st) {
   if (C != 128) return set_error("ag_pair_out_embed_fwd: built for pair dim 128 (got %d)", C);
-  const long cells = (long)B * P * P;
-  pair_out_embed_kernel<<<grid_for(cells * 32, 256, device), 256, 0, st>>>(pair, w, b, emb, out, B, P);
+  if (rows < 1 || P % rows) return set_error("ag_pair_out_embed_fwd: rows=%d must divide P=%d", rows, P);
+  const long cells = (long)B * rows * P;
+  pair_out_embed_kernel<<<grid_for(cells * 32, 256, device), 256, 0, st>>>(pair, pairT, w, b, emb, out, B, rows, P);
   return check_launch("ag_pair_out_embed_fwd");
 }
 

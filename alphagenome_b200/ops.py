@@ -224,8 +224,8 @@ def attention(
     a.scale, a.softcap = float(scale), float(softcap)
     if bias is not None:
         _f32(bias, "bias")
-        _require(bias.dim() == 4 and bias.shape[0] == B and bias.shape[1] == H and bias.shape[2] == bias.shape[3], "bias must be [B,H,P,P]")
-        a.bias, a.bias_p = bias.data_ptr(), bias.shape[2]
+        _require(bias.dim() == 4 and bias.shape[0] == B and bias.shape[1] == H, "bias must be [B,H,rows,cols]")
+        a.bias, a.bias_rows, a.bias_p = bias.data_ptr(), bias.shape[2], bias.shape[3]
     a.out = out.data_ptr()
     a.out_bstride, a.out_hstride, a.out_ld = st(out, 0), st(out, 1), out.stride(2)
     a.out_dtype = 0 if out.dtype == torch.bfloat16 else 1
@@ -266,12 +266,12 @@ def transpose_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
 
 
 def pair_bias(pair, scale, shift, W, bias_out) -> None:
-    B, P, _, Cc = pair.shape
+    B, rows, cols, Cc = pair.shape
     for t, nm in ((pair, "pair"), (scale, "scale"), (shift, "shift"), (W, "W"), (bias_out, "bias_out")):
         _f32(t, nm)
     heads = W.shape[0]
-    _require(tuple(bias_out.shape) == (B, heads, P, P), "bias_out must be [B, heads, P, P]")
-    _lib.check(_lib.load().ag_pair_bias_fwd(pair.data_ptr(), scale.data_ptr(), shift.data_ptr(), W.data_ptr(), bias_out.data_ptr(), B, P, Cc, heads, _dev(pair), _stream()))
+    _require(tuple(bias_out.shape) == (B, heads, rows, cols), "bias_out must be [B, heads, rows, cols]")
+    _lib.check(_lib.load().ag_pair_bias_fwd(pair.data_ptr(), scale.data_ptr(), shift.data_ptr(), W.data_ptr(), bias_out.data_ptr(), B, rows, cols, Cc, heads, _dev(pair), _stream()))
 
 
 def pool_rmsnorm(single, w, b, x_out, xg_out, pool: int) -> None:
@@ -283,15 +283,17 @@ def pool_rmsnorm(single, w, b, x_out, xg_out, pool: int) -> None:
     _lib.check(_lib.load().ag_pool_rmsnorm_fwd(single.data_ptr(), w.data_ptr(), b.data_ptr(), x_out.data_ptr(), xg_out.data_ptr(), B, n, Cc, pool, _dev(single), _stream()))
 
 
-def pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair_out, P: int) -> None:
-    B, H = qk.shape[0], qk.shape[1]
+def pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair_out, P: int, i_off: int = 0) -> None:
+    """qk/relq/prev/pair_out hold this rank's rows [i_off, i_off+rows); relk and outer hold all P rows."""
+    B, H, rows = qk.shape[0], qk.shape[1], qk.shape[2]
     D = Wp.shape[0]
     for t, nm in ((qk, "qk"), (relq, "relq"), (relk, "relk"), (Wp, "Wp"), (bp, "bp"), (outer, "outer"), (prev, "prev"), (pair_out, "pair_out")):
         _f32(t, nm)
-    _require(tuple(qk.shape[:3]) == (B, H, P) and tuple(relq.shape[:3]) == (B, H, P) and relk.shape == relq.shape, "qk/relq/relk must be [B,H,P,ld]")
-    _require(tuple(outer.shape) == (B, P, 2 * D) and tuple(pair_out.shape) == (B, P, P, D), "outer/pair_out shape mismatch")
+    _require(tuple(relq.shape[:3]) == (B, H, rows) and tuple(relk.shape[:3]) == (B, H, P) and relk.shape[3] == relq.shape[3], "relq [B,H,rows,ld], relk [B,H,P,ld]")
+    _require(tuple(outer.shape) == (B, P, 2 * D) and tuple(pair_out.shape) == (B, rows, P, D), "outer/pair_out shape mismatch")
+    _require(prev is None or prev.shape == pair_out.shape, "prev must match pair_out")
     _lib.check(_lib.load().ag_pair_combine_fwd(qk.data_ptr(), relq.data_ptr(), relk.data_ptr(), Wp.data_ptr(), bp.data_ptr(), outer.data_ptr(),
-                                               _ptr(prev), pair_out.data_ptr(), B, P, H, D, qk.shape[3], relq.shape[3], _dev(qk), _stream()))
+                                               _ptr(prev), pair_out.data_ptr(), B, P, H, D, qk.shape[3], relq.shape[3], rows, i_off, _dev(qk), _stream()))
 
 
 def rmsnorm(x, w, b, out) -> None:
@@ -311,8 +313,13 @@ def add_embed_norm(x, emb, scale, shift, single_out, a_out) -> None:
     _lib.check(_lib.load().ag_add_embed_norm_fwd(x.data_ptr(), emb.data_ptr(), scale.data_ptr(), shift.data_ptr(), single_out.data_ptr(), a_out.data_ptr(), B, rows, Cc, _dev(x), _stream()))
 
 
-def pair_out_embed(pair, w, b, emb, out) -> None:
-    B, P, _, Cc = pair.shape
-    for t, nm in ((pair, "pair"), (w, "w"), (b, "b"), (emb, "emb"), (out, "out")):
+def pair_out_embed(pair, w, b, emb, out, pairT=None) -> None:
+    """pair/out: this rank's rows [B, rows, P, C]; pairT: transposed blocks [P/rows, B, rows, rows, C] (None on one rank)."""
+    B, rows, P, Cc = pair.shape
+    if pairT is None:
+        _require(rows == P, "pairT is required for a row shard")
+        pairT = pair
+    for t, nm in ((pair, "pair"), (pairT, "pairT"), (w, "w"), (b, "b"), (emb, "emb"), (out, "out")):
         _f32(t, nm)
-    _lib.check(_lib.load().ag_pair_out_embed_fwd(pair.data_ptr(), w.data_ptr(), b.data_ptr(), emb.data_ptr(), out.data_ptr(), B, P, Cc, _dev(pair), _stream()))
+    _require(pairT.numel() == pair.numel(), "pairT size mismatch")
+    _lib.check(_lib.load().ag_pair_out_embed_fwd(pair.data_ptr(), pairT.data_ptr(), w.data_ptr(), b.data_ptr(), emb.data_ptr(), out.data_ptr(), B, rows, P, Cc, _dev(pair), _stream()))

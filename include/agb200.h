@@ -113,7 +113,7 @@ int ag_gemm_fwd(const AgGemmArgs* args, int device, void* stream);
  *   Q  bf16 [batch][heads][n_q][d]      addressed as b*q_bstride + h*q_hstride + i*q_ld + c
  *   K  bf16 [batch][kv_heads][n_k][d]   (kv_heads == 1: multi-query, shared by all heads)
  *   Vt bf16 [batch][kv_heads][dv][n_k]  (values TRANSPOSED: keys contiguous; v_ld = elements between dv rows)
- *   bias fp32 [batch][heads][bias_p][bias_p], bias_p >= n/16     (mode 0 only)
+ *   bias fp32 [batch][heads][bias_rows][bias_p]; rows index queries/16, columns keys/16     (mode 0 only)
  *   out [batch][heads][n_q][dv] addressed as b*out_bstride + h*out_hstride + i*out_ld + c; bf16 or fp32
  */
 typedef struct AgAttnArgs {
@@ -126,7 +126,7 @@ typedef struct AgAttnArgs {
   int32_t q_ld, k_ld, v_ld;
   int32_t batch, heads, kv_heads, n_q, n_k, d, dv;
   int32_t mode;       /* 0 = soft-capped + bias (AG:752-765), 1 = plain softmax (AG:880-885) */
-  int32_t bias_p;
+  int32_t bias_p;     /* bias columns (>= n_k/16) */
   float scale;        /* d^-0.5 */
   float softcap;      /* 5.0 (AG:653) */
   const float* bias;
@@ -136,6 +136,8 @@ typedef struct AgAttnArgs {
   int32_t out_dtype;  /* 0 = bf16, 1 = fp32 */
   const float* out_bias; /* [dv] fp32 or NULL (fp32 out only) */
   const float* res;      /* fp32, same addressing as out, or NULL (fp32 out only; may alias out) */
+  int32_t bias_rows;     /* bias rows (>= n_q/16); 0 = bias_p.  bias is [batch][heads][bias_rows][bias_p] */
+  int32_t reserved1;
 } AgAttnArgs;
 
 int ag_attention_fwd(const AgAttnArgs* args, int device, void* stream);
@@ -160,9 +162,10 @@ int ag_qkv_post_fwd(const float* qkv, void* Q, void* K, void* V, const float* co
 int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t C, int64_t in_bstride,
                       int32_t in_ld, int64_t out_bstride, int32_t out_ld, int device, void* stream);
 
-/* to_attn_bias (AG:688-693): bias[b][g][i][j] = sum_c W[g][c] * gelu_erf(pair[b][i][j][c]*scale[c] + shift[c]) */
+/* to_attn_bias (AG:688-693): bias[b][g][i][j] = sum_c W[g][c] * gelu_erf(pair[b][i][j][c]*scale[c] + shift[c]);
+ * pair is [B][rows][cols][C] (rows < cols for a sequence-parallel row shard), bias [B][heads][rows][cols] */
 int ag_pair_bias_fwd(const float* pair, const float* scale, const float* shift, const float* W, float* bias,
-                     int32_t B, int32_t P, int32_t C, int32_t heads, int device, void* stream);
+                     int32_t B, int32_t rows, int32_t cols, int32_t C, int32_t heads, int device, void* stream);
 
 /* SingleToPairwise prologue (AG:828-829, 852): mean over `pool` tokens -> RMSNormWithBias ->
  * x_bf16 [B][P][C] and gelu_erf(x) bf16 [B][P][C] */
@@ -171,10 +174,12 @@ int ag_pool_rmsnorm_fwd(const float* single, const float* w, const float* b, voi
 
 /* SingleToPairwise combine (AG:835-856): pair[b][i][j][:] = Wp . sim[b][i][j][:] + bp + outer[b][i][:D] +
  * outer[b][j][D:] (+ prev), with sim[..h] = qk[b][h][i][j] + 0.5*(relq[b][h][i][P+j-i] + relk[b][h][j][P+i-j]);
- * qk rows are qk_ld floats apart, relq/relk rows rel_ld floats apart (padded to the GEMM's N multiple of 16) */
+ * qk rows are qk_ld floats apart, relq/relk rows rel_ld floats apart (padded to the GEMM's N multiple of 16).
+ * Sequence-parallel row shard: this call produces global rows i in [i_off, i_off+rows); qk, relq, prev and pair hold
+ * only those rows ([B][H][rows][..] / [B][rows][P][D]); relk and outer hold all P rows. */
 int ag_pair_combine_fwd(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
                         const float* outer, const float* prev, float* pair, int32_t B, int32_t P, int32_t H,
-                        int32_t D, int32_t qk_ld, int32_t rel_ld, int device, void* stream);
+                        int32_t D, int32_t qk_ld, int32_t rel_ld, int32_t rows, int32_t i_off, int device, void* stream);
 
 /* RMSNormWithBias over the last dim (AG:400-405): fp32 [rows][C] -> bf16 [rows][C] */
 int ag_rmsnorm_fwd(const float* x, const float* w, const float* b, void* out_bf16, int64_t rows, int32_t C,
@@ -185,9 +190,11 @@ int ag_add_embed_norm_fwd(const float* x, const float* emb, const float* scale, 
                           float* single, void* a_bf16, int32_t B, int32_t rows, int32_t C, int device,
                           void* stream);
 
-/* OutputPairEmbedding (AG:1248-1259): out = gelu1702(RMSNormWithBias(0.5*(pair[b][i][j] + pair[b][j][i])) + emb[b]) */
-int ag_pair_out_embed_fwd(const float* pair, const float* w, const float* b, const float* emb, float* out,
-                          int32_t B, int32_t P, int32_t C, int device, void* stream);
+/* OutputPairEmbedding (AG:1248-1259): out = gelu1702(RMSNormWithBias(0.5*(pair[b][i][j] + pair[b][j][i])) + emb[b]).
+ * pair/out are this rank's rows [B][rows][P][C]; pairT holds the transposed blocks [P/rows][B][rows][rows][C] with
+ * pairT[s][b][jl][il] = pair_global[b][s*rows + jl][i_off + il] (one rank: rows == P and pairT == pair). */
+int ag_pair_out_embed_fwd(const float* pair, const float* pairT, const float* w, const float* b, const float* emb,
+                          float* out, int32_t B, int32_t rows, int32_t P, int32_t C, int device, void* stream);
 
 /* library / error plumbing */
 int ag_version(void);

@@ -1,0 +1,55 @@
+"""Three representative ag_gemm_fwd launches with their real epilogues (for `ncu --set full -k regex:gemm_conv`)."""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch
+
+from alphagenome_b200 import ops
+from alphagenome_b200.ops import ACT_GELU1702, Act
+
+dev = "cuda"
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+C = 768
+f32 = dict(device=dev, dtype=torch.float32)
+bf = dict(device=dev, dtype=torch.bfloat16)
+s, t = torch.rand(C, **f32) + 0.5, torch.randn(C, **f32)
+bias = torch.randn(C, **f32)
+
+
+def timeit(fn, name, flops):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"{name}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
+# (1) embed: K=64 -> out f32 + actA bf16
+X = torch.randn(1, M, 64, **f32).to(torch.bfloat16)
+W0 = (torch.randn(1, C, 64, **f32) * 0.1).to(torch.bfloat16)
+x0 = torch.empty(1, M, C, **f32)
+a0 = torch.empty(1, M, C, **bf)
+timeit(lambda: ops.gemm(X, W0, pre_shift=bias, out=x0, actA=Act(a0, s, t, ACT_GELU1702)), "embed_k64", 2.0 * M * C * 64)
+# (2) conv5 768->768 with res + actA + pool + actP (DNAEmbed.pointwise / DownresBlock.conv_out epilogue)
+W5 = (torch.randn(5, C, C, **f32) * 0.02).to(torch.bfloat16)
+skipact = torch.empty(1, M, C, **bf)
+xp = torch.empty(1, M // 2, C, **f32)
+ap = torch.empty(1, M // 2, C, **bf)
+timeit(lambda: ops.gemm(a0, W5, pre_shift=bias, res=x0, actA=Act(skipact, s, t, ACT_GELU1702), pool=xp, actP=Act(ap, s, t, ACT_GELU1702)),
+       "conv5_pool", 2.0 * M * C * C * 5)
+# (3) w1 768->768 with upsampled residual + out + actA (UpresBlock.unet_conv epilogue)
+W1 = (torch.randn(1, C, C, **f32) * 0.05).to(torch.bfloat16)
+low = torch.randn(1, M // 2, C, **f32)
+y = torch.empty(1, M, C, **f32)
+ay = torch.empty(1, M, C, **bf)
+timeit(lambda: ops.gemm(skipact, W1, pre_shift=bias, res=low, res_shift=1, out=y, actA=Act(ay, s, t, ACT_GELU1702)), "w1_upres", 2.0 * M * C * C)
+# (4) conv5 768->768 res + out + actA (UpresBlock.conv_out)
+timeit(lambda: ops.gemm(ay, W5, pre_shift=bias, res=y, out=x0, actA=Act(a0, s, t, ACT_GELU1702)), "conv5_out", 2.0 * M * C * C * 5)
