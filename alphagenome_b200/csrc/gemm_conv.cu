@@ -41,6 +41,13 @@ struct GemmKParams {
 };
 
 // One activated output for 4 consecutive channels of one row (scale/shift pre-loaded per chunk).
+// Only ACT_NONE / ACT_GELU1702 occur in GEMM epilogues (checked on the host): one uniform branch per 4 elements.
+__device__ __forceinline__ float gelu1702_fast(float x) {   // 0.5x + 0.5x*tanh(0.851x): one MUFU op
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(0.851f * x), hx);
+}
+__device__ __forceinline__ float gelu1702_acc(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+
 __device__ __forceinline__ void epi_store4(const AgEpiOut& o, long off, float4 v, const float4& s, const float4& t) {
   float4 y;
   y.x = fmaf(v.x, s.x, t.x);
@@ -48,10 +55,12 @@ __device__ __forceinline__ void epi_store4(const AgEpiOut& o, long off, float4 v
   y.z = fmaf(v.z, s.z, t.z);
   y.w = fmaf(v.w, s.w, t.w);
   if (o.dtype == 0) {
-    y.x = act_apply_fast(y.x, o.act);
-    y.y = act_apply_fast(y.y, o.act);
-    y.z = act_apply_fast(y.z, o.act);
-    y.w = act_apply_fast(y.w, o.act);
+    if (o.act != ACT_NONE) {
+      y.x = gelu1702_fast(y.x);
+      y.y = gelu1702_fast(y.y);
+      y.z = gelu1702_fast(y.z);
+      y.w = gelu1702_fast(y.w);
+    }
     __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y);
     __nv_bfloat162 hi = __floats2bfloat162_rn(y.z, y.w);
     uint2 pk;
@@ -59,10 +68,12 @@ __device__ __forceinline__ void epi_store4(const AgEpiOut& o, long off, float4 v
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(o.ptr) + off) = pk;
   } else {
-    y.x = act_apply(y.x, o.act);
-    y.y = act_apply(y.y, o.act);
-    y.z = act_apply(y.z, o.act);
-    y.w = act_apply(y.w, o.act);
+    if (o.act != ACT_NONE) {
+      y.x = gelu1702_acc(y.x);
+      y.y = gelu1702_acc(y.y);
+      y.z = gelu1702_acc(y.z);
+      y.w = gelu1702_acc(y.w);
+    }
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.ptr) + off) = y;
   }
 }
@@ -198,6 +209,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kMaxNTile;
 
       for (int ch = half; ch < nchunks; ch += 2) {
+        const int c = n0 + ch * kEpiCols + 4 * cg;
+        // ---- global loads first: residual rows and per-channel parameters are in flight while the
+        //      accumulators travel TMEM -> registers -> smem ----
+        const bool has_res = (g.res != nullptr) && (c < g.res_ch);
+        float4 rr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = r_base + 2 * rsel + (k & 1) + 16 * (k >> 1);
+          rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && row < g.M)
+            rr[k] = __ldg(reinterpret_cast<const float4*>(g.res + (long)b * g.res_bstride + (long)(row >> g.res_shift) * g.res_ld + c));
+        }
+        const float4 ps = ldg4_or(g.pre_scale, c, 1.0f);
+        const float4 pt = ldg4_or(g.pre_shift, c, 0.0f);
+        float4 sA, tA, sB, tB, sP, tP;
+        if (g.actA.ptr) { sA = ldg4_or(g.actA.scale, c, 1.0f); tA = ldg4_or(g.actA.shift, (long)b * g.actA.shift_bstride + c, 0.0f); }
+        if (g.actB.ptr) { sB = ldg4_or(g.actB.scale, c, 1.0f); tB = ldg4_or(g.actB.shift, (long)b * g.actB.shift_bstride + c, 0.0f); }
+        if (g.actP.ptr) { sP = ldg4_or(g.actP.scale, c, 1.0f); tP = ldg4_or(g.actP.shift, (long)b * g.actP.shift_bstride + c, 0.0f); }
+
         uint32_t r[16];
         tmem_ld_32x16(t_addr + (uint32_t)(ch * kEpiCols), r);
         tmem_ld_wait();
@@ -206,15 +236,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           *reinterpret_cast<uint4*>(stg + lane * kEpiStride + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
 
-        const int c = n0 + ch * kEpiCols + 4 * cg;
-        const float4 ps = ldg4_or(g.pre_scale, c, 1.0f);
-        const float4 pt = ldg4_or(g.pre_shift, c, 0.0f);
-        float4 sA, tA, sB, tB, sP, tP;
-        if (g.actA.ptr) { sA = ldg4_or(g.actA.scale, c, 1.0f); tA = ldg4_or(g.actA.shift, (long)b * g.actA.shift_bstride + c, 0.0f); }
-        if (g.actB.ptr) { sB = ldg4_or(g.actB.scale, c, 1.0f); tB = ldg4_or(g.actB.shift, (long)b * g.actB.shift_bstride + c, 0.0f); }
-        if (g.actP.ptr) { sP = ldg4_or(g.actP.scale, c, 1.0f); tP = ldg4_or(g.actP.shift, (long)b * g.actP.shift_bstride + c, 0.0f); }
-        const bool has_res = (g.res != nullptr) && (c < g.res_ch);
-
+        const long out_base = (long)b * g.out_bstride + c;
+        const long a_base = (long)b * g.actA.bstride + c;
+        const long b_base = (long)b * g.actB.bstride + c;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float4 v[2];
@@ -223,20 +247,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             const int lr = 2 * rsel + h + 16 * i;
             const int row = r_base + lr;
             float4 x = *reinterpret_cast<const float4*>(stg + lr * kEpiStride + 4 * cg);
+            const float4 ra = rr[i * 2 + h];
             x.x = fmaf(x.x, ps.x, pt.x);
             x.y = fmaf(x.y, ps.y, pt.y);
             x.z = fmaf(x.z, ps.z, pt.z);
             x.w = fmaf(x.w, ps.w, pt.w);
             if (g.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            x.x = (x.x + ra.x) * post;
+            x.y = (x.y + ra.y) * post;
+            x.z = (x.z + ra.z) * post;
+            x.w = (x.w + ra.w) * post;
             if (row < g.M) {
-              if (has_res) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(g.res + (long)b * g.res_bstride + (long)(row >> g.res_shift) * g.res_ld + c));
-                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-              }
-              x.x *= post; x.y *= post; x.z *= post; x.w *= post;
-              if (g.out) *reinterpret_cast<float4*>(g.out + (long)b * g.out_bstride + (long)row * g.out_ld + c) = x;
-              if (g.actA.ptr) epi_store4(g.actA, (long)b * g.actA.bstride + (long)row * g.actA.ld + c, x, sA, tA);
-              if (g.actB.ptr) epi_store4(g.actB, (long)b * g.actB.bstride + (long)row * g.actB.ld + c, x, sB, tB);
+              if (g.out) *reinterpret_cast<float4*>(g.out + out_base + (long)row * g.out_ld) = x;
+              if (g.actA.ptr) epi_store4(g.actA, a_base + (long)row * g.actA.ld, x, sA, tA);
+              if (g.actB.ptr) epi_store4(g.actB, b_base + (long)row * g.actB.ld, x, sB, tB);
             }
             v[h] = x;
           }
@@ -305,6 +329,7 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
         (reinterpret_cast<uintptr_t>(o->scale) & 15) || (reinterpret_cast<uintptr_t>(o->shift) & 15))
       return set_error("ag_gemm_fwd: activated outputs need ld/bstride multiples of 4 and aligned pointers");
     if (o->dtype != 0 && o->dtype != 1) return set_error("ag_gemm_fwd: bad output dtype %d", o->dtype);
+    if (o->act != AG_ACT_NONE && o->act != AG_ACT_GELU1702) return set_error("ag_gemm_fwd: epilogue activations are AG_ACT_NONE or AG_ACT_GELU1702 (got %d)", o->act);
   }
   if ((reinterpret_cast<uintptr_t>(a.pre_scale) | reinterpret_cast<uintptr_t>(a.pre_shift)) & 15)
     return set_error("ag_gemm_fwd: pre_scale/pre_shift must be 16-byte aligned");

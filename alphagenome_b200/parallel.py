@@ -1,0 +1,150 @@
+"""Sequence-parallel plumbing for the trunk forward (one process per GPU, torch.distributed / NCCL over NVLink).
+
+The reference has no sequence parallelism; this is new work.  Partitioning of a length-L
+context over G ranks (contiguous, L/G a multiple of 2048 bp so every pool-2 pair, 128 bp token and 16-token pair
+bin is rank-local):
+
+  rank r owns bp [r L/G, (r+1) L/G)  ->  tokens [r n/G, ...)  ->  pair ROWS [r P/G, ...) x all P columns.
+
+  conv encoder / decoder   each rank runs the convs on its window EXTENDED by `halo_bp` real bases on each
+                           interior side and crops.  A w5 conv contaminates 2 positions per layer from a cut
+                           edge: 513 bp through the encoder, +762 bp through the decoder = 1275 bp < 2048 bp, so
+                           everything inside the owned range is exact; at the two true sequence ends there is no
+                           halo and the window edge IS the reference's zero padding.  Costs 2*2048/(L/G) extra
+                           conv work (3 % at 1 Mbp / 8 GPUs) and only ONE exchange (16 tower-output tokens per
+                           side) instead of 27 per-layer halo exchanges.
+  tower attention          Q local; K [n,128] and V [n,192] all-gathered per layer (bf16).  Bias rows are local.
+  pair blocks              pooled/normalised single rows all-gathered (bf16 [P,1536] x2); q.k and rel-pos GEMMs,
+                           row attention, FF and the bias projection run on local rows only.
+  pair output embedding    symmetrize needs pair[j, i]: one all_to_all of [P/G x P/G] blocks.
+
+Every helper below is device-agnostic (the CPU/gloo tests in tests/test_parallel_cpu.py run them with
+world_size 2).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+HALO_BP = 2048  # >= 1275 bp (encoder 513 + decoder 762 receptive-field radius), multiple of 128
+TOKEN_BP = 128
+PAIR_BP = 2048
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    rank: int
+    world: int
+    L: int            # global context length (bp)
+    start: int        # owned bp range [start, end)
+    end: int
+    halo_left: int    # bp of real halo on each side of the window (0 at a true sequence end)
+    halo_right: int
+
+    @property
+    def win_start(self) -> int:
+        return self.start - self.halo_left
+
+    @property
+    def win_end(self) -> int:
+        return self.end + self.halo_right
+
+    @property
+    def L_loc(self) -> int:
+        return self.end - self.start
+
+    @property
+    def n_loc(self) -> int:
+        return self.L_loc // TOKEN_BP
+
+    @property
+    def n(self) -> int:
+        return self.L // TOKEN_BP
+
+    @property
+    def tok_off(self) -> int:
+        return self.start // TOKEN_BP
+
+    @property
+    def halo_tok_left(self) -> int:
+        return self.halo_left // TOKEN_BP
+
+    @property
+    def halo_tok_right(self) -> int:
+        return self.halo_right // TOKEN_BP
+
+    @property
+    def P(self) -> int:
+        return self.L // PAIR_BP
+
+    @property
+    def P_loc(self) -> int:
+        return self.L_loc // PAIR_BP
+
+    @property
+    def row_off(self) -> int:
+        return self.start // PAIR_BP
+
+
+def shard_plan(L: int, world: int, rank: int, halo_bp: int = HALO_BP) -> ShardPlan:
+    if L % (PAIR_BP * world) != 0:
+        raise ValueError(f"context length {L} must be a multiple of {PAIR_BP} * world_size ({world})")
+    if halo_bp % TOKEN_BP != 0:
+        raise ValueError("halo must be a whole number of 128 bp tokens")
+    L_loc = L // world
+    if world > 1 and halo_bp > L_loc:
+        raise ValueError(f"halo {halo_bp} bp exceeds the shard length {L_loc} bp")
+    start = rank * L_loc
+    return ShardPlan(rank=rank, world=world, L=L, start=start, end=start + L_loc,
+                     halo_left=halo_bp if rank > 0 else 0, halo_right=halo_bp if rank < world - 1 else 0)
+
+
+class SeqParallel:
+    """Collectives used by TrunkEngine in sequence-parallel mode."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, halo_bp: int = HALO_BP):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.halo_bp = halo_bp
+        self.n_collectives = 0
+
+    def plan(self, L: int) -> ShardPlan:
+        return shard_plan(L, self.world, self.rank, self.halo_bp)
+
+    def gather_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """x: [B, rows_loc, C] (same shape on every rank) -> [B, world*rows_loc, C] in rank order."""
+        x = x.contiguous()
+        B, r, C = x.shape
+        out = torch.empty(self.world, B, r, C, dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group)
+        self.n_collectives += 1
+        if B == 1:
+            return out.view(1, self.world * r, C)
+        return out.permute(1, 0, 2, 3).reshape(B, self.world * r, C)
+
+    def exchange_halo(self, x: torch.Tensor, h: int):
+        """x: [B, rows, C]; returns (left, right): the last h rows of rank-1 and the first h rows of rank+1
+        (None at the two sequence ends)."""
+        B, r, C = x.shape
+        edges = torch.stack((x[:, :h], x[:, r - h:]), dim=0).contiguous()  # [2, B, h, C]
+        out = torch.empty(self.world, 2, B, h, C, dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out.view(-1), edges.view(-1), group=self.group)
+        self.n_collectives += 1
+        left = out[self.rank - 1, 1] if self.rank > 0 else None
+        right = out[self.rank + 1, 0] if self.rank < self.world - 1 else None
+        return left, right
+
+    def transpose_blocks(self, pair: torch.Tensor) -> torch.Tensor:
+        """pair: this rank's rows [B, P_loc, P, C] -> pairT [world, B, P_loc, P_loc, C] with
+        pairT[s, b, jl, il] = pair_global[b, s*P_loc + jl, row_off + il]  (the layout ag_pair_out_embed_fwd reads)."""
+        B, Pl, P, C = pair.shape
+        G = self.world
+        send = pair.view(B, Pl, G, Pl, C).permute(2, 0, 1, 3, 4).contiguous()  # [dest s, B, il, jl(cols of s), C]
+        recv = torch.empty_like(send)                                          # [src s, B, jl (rows of s), il (my cols), C]
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+        self.n_collectives += 1
+        return recv

@@ -51,6 +51,7 @@ class TrunkEngine:
         self._rope: Dict = {}
         self._rel: Dict = {}
         self.collect = None  # optional callback(name, tensor) for per-stage parity tests
+        self.sp = None       # alphagenome_b200.parallel.SeqParallel when the context is sharded over ranks
 
     # ------------------------------------------------------------------------------------------ packing
     def _version_key(self, device):
@@ -228,18 +229,24 @@ class TrunkEngine:
             self._note(f"downs.{i}.pooled", x)
         return x, skips
 
-    def _pair_block(self, P, li, single, pair):
+    def _pair_block(self, P, li, single, pair, plan=None):
+        """SingleToPairwise + row attention + pair FF (AG:1019-1022).  With a ShardPlan, `single` holds this rank's
+        tokens and `pair` its rows [B, P_loc, P, 128]; pooled rows are all-gathered, everything else is row-local."""
         L = P["layers"][li]
         sp, pa, pf = L["s2p"], L["pattn"], L["pff"]
-        B, n, D = single.shape
+        B, n_loc, D = single.shape
         dev = single.device
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         pool, H, dp = sp["pool"], sp["heads"], sp["dp"]
-        Pn = n // pool
-        xs = torch.empty(B, Pn, D, **bf)
-        xg = torch.empty(B, Pn, D, **bf)
-        ops.pool_rmsnorm(single, sp["nw"], sp["nb"], xs, xg, pool)
+        Pl = n_loc // pool                      # local rows
+        xsg = torch.empty(2, B, Pl, D, **bf)    # [0] normalised pooled rows, [1] their erf-GELU
+        ops.pool_rmsnorm(single, sp["nw"], sp["nb"], xsg[0], xsg[1], pool)
+        if plan is not None and plan.world > 1:
+            g = self.sp.gather_rows(xsg.view(2 * B, Pl, D)).view(2, B, plan.P, D)
+            xs, xg, Pn, i0 = g[0], g[1], plan.P, plan.row_off
+        else:
+            xs, xg, Pn, i0 = xsg[0], xsg[1], Pl, 0
         qk_plain = torch.empty(B, Pn, 2 * H * dp, **bf)
         qk_bias = torch.empty(B, Pn, 2 * H * dp, **bf)
         ops.gemm(xs, sp["Wqk"], actA=Act(qk_plain), actB=Act(qk_bias, None, sp["relbias"]))
@@ -247,24 +254,24 @@ class TrunkEngine:
         ops.gemm(xg, sp["Wouter"], out=outer)
         R = self.rel_encoding(li, Pn, dev).view(2 * Pn, H, dp).permute(1, 0, 2)  # [H, 2P, dp] view
         Np, N2 = _round_up(Pn, 16), _round_up(2 * Pn, 16)
-        qk_out = torch.empty(B, H, Pn, Np, **f32)
-        relq = torch.empty(B, H, Pn, N2, **f32)
+        qk_out = torch.empty(B, H, Pl, Np, **f32)
+        relq = torch.empty(B, H, Pl, N2, **f32)
         relk = torch.empty(B, H, Pn, N2, **f32)
         for b in range(B):
-            qp = qk_plain[b, :, : H * dp].view(Pn, H, dp).permute(1, 0, 2)
+            qp = qk_plain[b, i0:i0 + Pl, : H * dp].view(Pl, H, dp).permute(1, 0, 2)
             kp = qk_plain[b, :, H * dp:].view(Pn, H, dp).permute(1, 0, 2)
-            qb = qk_bias[b, :, : H * dp].view(Pn, H, dp).permute(1, 0, 2)
+            qb = qk_bias[b, i0:i0 + Pl, : H * dp].view(Pl, H, dp).permute(1, 0, 2)
             kb = qk_bias[b, :, H * dp:].view(Pn, H, dp).permute(1, 0, 2)
             ops.gemm(qp, kp, w_batched=True, n_pad=Np, out=qk_out[b])       # q_i . k_j            (AG:835)
             ops.gemm(qb, R, w_batched=True, n_pad=N2, out=relq[b])          # (q_i + bq) . R[p]    (AG:843)
             ops.gemm(kb, R, w_batched=True, n_pad=N2, out=relk[b])          # (k_j + bk) . R[p]    (AG:844)
-        new_pair = torch.empty(B, Pn, Pn, dp, **f32)
-        ops.pair_combine(qk_out, relq, relk, sp["Wp"], sp["bp"], outer, pair, new_pair, P=Pn)
+        new_pair = torch.empty(B, Pl, Pn, dp, **f32)
+        ops.pair_combine(qk_out, relq, relk, sp["Wp"], sp["bp"], outer, pair, new_pair, P=Pn, i_off=i0)
         pair = new_pair
         del qk_out, relq, relk, qk_plain, qk_bias
         self._note(f"tower.layer{li}.pair_s2p", pair)
-        # --- row attention (AG:1021) ---
-        cells = B * Pn * Pn
+        # --- row attention (AG:1021): attends over the second index, so a row shard is self-contained ---
+        cells = B * Pl * Pn
         pn = torch.empty(1, cells, dp, **bf)
         ops.rmsnorm(pair, pa["nw"], pa["nb"], pn)
         qkp = torch.empty(1, cells, 2 * dp, **bf)
@@ -272,10 +279,10 @@ class TrunkEngine:
         vp = torch.empty(1, cells, dp, **bf)
         ops.gemm(pn, pa["Wv"], actA=Act(vp))
         Pk = _round_up(Pn, 8)
-        vpt = torch.zeros(B * Pn, dp, Pk, **bf) if Pk != Pn else torch.empty(B * Pn, dp, Pk, **bf)
-        ops.transpose_bf16(vp.view(B * Pn, Pn, dp), vpt)
-        q4 = qkp.view(B, Pn, Pn, 2 * dp)
-        ops.attention(q4[..., :dp], q4[..., dp:], vpt.view(B, Pn, dp, Pk), pair, mode=1, scale=pa["scale"],
+        vpt = torch.zeros(B * Pl, dp, Pk, **bf) if Pk != Pn else torch.empty(B * Pl, dp, Pk, **bf)
+        ops.transpose_bf16(vp.view(B * Pl, Pn, dp), vpt)
+        q4 = qkp.view(B, Pl, Pn, 2 * dp)
+        ops.attention(q4[..., :dp], q4[..., dp:], vpt.view(B, Pl, dp, Pk), pair, mode=1, scale=pa["scale"],
                       out_bias=pa["bv"], res=pair)
         self._note(f"tower.layer{li}.pair_attn", pair)
         # --- pair feed-forward (AG:1022) ---
@@ -286,28 +293,30 @@ class TrunkEngine:
         ops.gemm(hid, pf["W2"], pre_shift=pf["b2"], res=pflat, out=pflat)
         return pair
 
-    def _tower(self, P, x, org_embed, final_act: Act, final_plain: Optional[torch.Tensor]):
-        """x: fp32 [B, n, D] pooled encoder output.  Returns (single fp32, pair fp32)."""
+    def _tower(self, P, x, org_embed, final_act: Act, final_plain: Optional[torch.Tensor], plan=None):
+        """x: fp32 [B, n_loc, D] pooled encoder output (this rank's tokens).  Returns (single fp32, pair fp32)."""
         B, n, D = x.shape
         dev = x.device
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         layers = P["layers"]
         tw = self.unet().transformer
-        if n > tw.max_positions:
-            raise ops._lib.AgbError(f"{n} tokens exceed max_positions={tw.max_positions} (AG:538, 922)")
+        sharded = plan is not None and plan.world > 1
+        n_all = plan.n if sharded else n
+        if n_all > tw.max_positions:
+            raise ops._lib.AgbError(f"{n_all} tokens exceed max_positions={tw.max_positions} (AG:538, 922)")
         single = torch.empty(B, n, D, **f32)
         a = torch.empty(B, n, D, **bf)
         s0, t0 = layers[0]["attn"]["pre"]
         if org_embed is None:
             org_embed = torch.zeros(B, D, **f32)
         ops.add_embed_norm(x, org_embed.to(torch.float32).contiguous(), s0, t0, single, a)
-        cos_t, sin_t = self.rope_tables(n, dev)
+        cos_t, sin_t = self.rope_tables(n, dev, offset=plan.tok_off if sharded else 0)
         pair = None
         a_ff = torch.empty(B, n, D, **bf)
         for li, L in enumerate(layers):
             if "s2p" in L:
-                pair = self._pair_block(P, li, single, pair)
+                pair = self._pair_block(P, li, single, pair, plan)
             at = L["attn"]
             Hh, d, dv = at["heads"], at["d"], at["dv"]
             qkv = torch.empty(B, n, Hh * d + d + dv, **f32)
@@ -316,14 +325,16 @@ class TrunkEngine:
             K = torch.empty(B, n, d, **bf)
             V = torch.empty(B, n, dv, **bf)
             ops.qkv_post(qkv, Q, K, V, cos_t, sin_t, at["qw"], at["qb"], at["kw"], at["kb"], at["vw"], at["vb"], Hh, d, dv)
-            nk = _round_up(n, 8)
+            if sharded:  # K/V of every rank (AG:748 attends over the whole context); Q and the bias rows stay local
+                K = self.sp.gather_rows(K)
+                V = self.sp.gather_rows(V)
+            nk = _round_up(n_all, 8)
             Vt = torch.empty(B, dv, nk, **bf)
             ops.transpose_bf16(V, Vt)
-            Pn = pair.shape[1]
-            bias = torch.empty(B, Hh, Pn, Pn, **f32)
+            bias = torch.empty(B, Hh, pair.shape[1], pair.shape[2], **f32)
             ops.pair_bias(pair, at["ab_s"], at["ab_t"], at["ab_W"], bias)
             O = torch.empty(B, n, Hh * dv, **bf)
-            ops.attention(Q.view(B, n, Hh, d).permute(0, 2, 1, 3), K.view(B, 1, n, d), Vt.view(B, 1, dv, nk),
+            ops.attention(Q.view(B, n, Hh, d).permute(0, 2, 1, 3), K.view(B, 1, n_all, d), Vt.view(B, 1, dv, nk),
                           O.view(B, n, Hh, dv).permute(0, 2, 1, 3), mode=0, scale=at["scale"], bias=bias, softcap=at["softcap"])
             ff = L["ff"]
             ops.gemm(O, at["Wout"], pre_scale=at["out_scale"], pre_shift=at["out_shift"], res=single, out=single,
@@ -376,19 +387,41 @@ class TrunkEngine:
     # ------------------------------------------------------------------------------------------ public
     @torch.no_grad()
     def run(self, seq, org_embed, organism_index=None, with_embeds=False):
+        """seq: int64 [B, L] — the WHOLE context on every rank.  With `self.sp` set (sequence parallel) each rank
+        computes and returns only its shard: bp [r L/G, (r+1) L/G), the matching tokens, and its pair rows."""
         if not seq.is_cuda:
             raise ops._lib.AgbError("alphagenome_b200 has no CPU path: inputs must be CUDA tensors on a B200")
-        seq = seq.to(torch.int64).contiguous()
         dev = seq.device
         P = self.pack(dev)
         bf = dict(device=dev, dtype=torch.bfloat16)
+        plan = self.sp.plan(seq.shape[1]) if self.sp is not None else None
+        sharded = plan is not None and plan.world > 1
+        if sharded:
+            seq = seq[:, plan.win_start:plan.win_end]
+        seq = seq.to(torch.int64).contiguous()
         x, skips = self._encoder(P, seq)
+        hl, hr = (plan.halo_tok_left, plan.halo_tok_right) if sharded else (0, 0)
+        if sharded:
+            x = x[:, hl:hl + plan.n_loc].contiguous()  # the halo tokens only existed to make the owned ones exact
         B, n, D = x.shape
         u0 = P["ups"][0]["conv"]
         a_dec = torch.empty(B, n, D, **bf)
         single_b16 = torch.empty(B, n, D, **bf) if with_embeds else None
-        single, pair = self._tower(P, x, org_embed, Act(a_dec, u0["s"], u0["t"], ACT_GELU1702), single_b16)
-        unet_out, unet_b16 = self._decoder(P, single, a_dec, skips, want_plain=with_embeds)
+        single, pair = self._tower(P, x, org_embed, Act(a_dec, u0["s"], u0["t"], ACT_GELU1702), single_b16, plan)
+        x_dec = single
+        if sharded:
+            # the decoder's receptive field reaches 6 tokens into the neighbours: fetch halo tokens of the tower
+            # output (fp32 residual + the pre-activated bf16 operand) and run the decoder on the extended window
+            ht = self.sp.halo_bp // 128
+            l32, r32 = self.sp.exchange_halo(single, ht)
+            l16, r16 = self.sp.exchange_halo(a_dec, ht)
+            x_dec = torch.cat([t for t in (l32, single, r32) if t is not None], dim=1)
+            a_dec = torch.cat([t for t in (l16, a_dec, r16) if t is not None], dim=1)
+        unet_out, unet_b16 = self._decoder(P, x_dec, a_dec, skips, want_plain=with_embeds)
+        if sharded:
+            unet_out = unet_out[:, plan.halo_left:plan.halo_left + plan.L_loc]
+            if unet_b16 is not None:
+                unet_b16 = unet_b16[:, plan.halo_left:plan.halo_left + plan.L_loc]
         out = dict(unet_output=unet_out, single_repr=single, pairwise_repr=pair)
         if with_embeds:
             f32 = dict(device=dev, dtype=torch.float32)
@@ -407,7 +440,8 @@ class TrunkEngine:
             e1 = torch.empty(B, Lfull, o1["W"].shape[1], **f32)
             ops.gemm(unet_b16, o1["W"], pre_shift=o1["b"], res=skp, res_shift=shift, actA=Act(e1, o1["s"], t1, ACT_GELU1702))
             epair = torch.empty_like(pair)
-            ops.pair_out_embed(pair, op["w"], op["b"], op["emb"].index_select(0, organism_index).contiguous(), epair)
+            pairT = self.sp.transpose_blocks(pair) if sharded else None  # symmetrize needs pair[j, i] (AG:1253)
+            ops.pair_out_embed(pair, op["w"], op["b"], op["emb"].index_select(0, organism_index).contiguous(), epair, pairT=pairT)
             out.update(embeds_1bp=e1, embeds_128bp=e128, embeds_pair=epair)
         return out
 

@@ -64,7 +64,7 @@ typedef struct AgEpiOut {
  *   v = acc * pre_scale[n] + pre_shift[n];  if relu: v = max(v, 0)
  *   if res && n < res_ch: v += res[b, r >> res_shift, n]
  *   if post_scale: v *= *post_scale
- *   out[b, r, n] = v;  actA / actB[b, r, n] = act(v * scale + shift)
+ *   out[b, r, n] = v;  actA / actB[b, r, n] = act(v * scale + shift)        (act: AG_ACT_NONE or AG_ACT_GELU1702)
  *   pool[b, r/2, n] = max(v[r], v[r^1]);  actP[b, r/2, n] = act(pool * scale + shift)      (maxpool2, AG:468)
  *
  * A rows outside [0, a_rows) read as zero (the conv's zero padding, AG:448); rows are addressed as
