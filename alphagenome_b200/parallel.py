@@ -111,6 +111,18 @@ class SeqParallel:
         self.world = dist.get_world_size(group)
         self.halo_bp = halo_bp
         self.n_collectives = 0
+        # NCCL moves device buffers directly over NVLink.  With the gloo backend (CPU tests; the 2-process
+        # single-GPU parity test) device tensors are staged through host memory — test plumbing only.
+        self._stage = dist.get_backend(group) == "gloo"
+
+    def _all_gather(self, out: torch.Tensor, x: torch.Tensor) -> None:
+        if self._stage and x.is_cuda:
+            o = torch.empty(out.shape, dtype=out.dtype)
+            dist.all_gather_into_tensor(o.view(-1), x.cpu().view(-1), group=self.group)
+            out.copy_(o)
+        else:
+            dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group)
+        self.n_collectives += 1
 
     def plan(self, L: int) -> ShardPlan:
         return shard_plan(L, self.world, self.rank, self.halo_bp)
@@ -120,8 +132,7 @@ class SeqParallel:
         x = x.contiguous()
         B, r, C = x.shape
         out = torch.empty(self.world, B, r, C, dtype=x.dtype, device=x.device)
-        dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group)
-        self.n_collectives += 1
+        self._all_gather(out, x)
         if B == 1:
             return out.view(1, self.world * r, C)
         return out.permute(1, 0, 2, 3).reshape(B, self.world * r, C)
@@ -132,8 +143,7 @@ class SeqParallel:
         B, r, C = x.shape
         edges = torch.stack((x[:, :h], x[:, r - h:]), dim=0).contiguous()  # [2, B, h, C]
         out = torch.empty(self.world, 2, B, h, C, dtype=x.dtype, device=x.device)
-        dist.all_gather_into_tensor(out.view(-1), edges.view(-1), group=self.group)
-        self.n_collectives += 1
+        self._all_gather(out, edges)
         left = out[self.rank - 1, 1] if self.rank > 0 else None
         right = out[self.rank + 1, 0] if self.rank < self.world - 1 else None
         return left, right
@@ -145,6 +155,11 @@ class SeqParallel:
         G = self.world
         send = pair.view(B, Pl, G, Pl, C).permute(2, 0, 1, 3, 4).contiguous()  # [dest s, B, il, jl(cols of s), C]
         recv = torch.empty_like(send)                                          # [src s, B, jl (rows of s), il (my cols), C]
-        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+        if self._stage and send.is_cuda:
+            r = torch.empty(send.shape, dtype=send.dtype)
+            dist.all_to_all_single(r.view(-1), send.cpu().view(-1), group=self.group)
+            recv.copy_(r)
+        else:
+            dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
         self.n_collectives += 1
         return recv

@@ -1,0 +1,71 @@
+"""Sequence-parallel parity check, launched with torchrun (one process per rank):
+
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sp_check.py --length 32768
+    ... --same-gpu   # both ranks on cuda:0 over gloo (host-staged collectives) — lets a 1-GPU box cover the path
+
+Every rank runs the sharded forward; rank 0 also runs the unsharded forward and compares the gathered shards."""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from alphagenome_b200.init_weights import apply_synth_weights
+from alphagenome_b200.model import AlphaGenome
+from alphagenome_b200.parallel import SeqParallel
+from alphagenome_b200.trunk import engine_for
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--length", type=int, default=32768)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--same-gpu", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", 0 if args.same_gpu else local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo" if args.same_gpu else "nccl")
+    model = AlphaGenome().to(dev).eval()
+    apply_synth_weights(model, seed=4)
+    B, L = args.batch, args.length
+    seq = torch.from_numpy(np.random.default_rng(11).integers(0, 4, size=(B, L)).astype(np.int64))
+    seq[0, 7] = -1
+    seq = seq.to(dev)
+    org = (torch.arange(B) % 2).to(dev)
+    eng = engine_for(model.transformer_unet, model)
+    eng.sp = SeqParallel()
+    emb, tu = model.get_embeds(seq, org, return_unet_transformer_outputs=True)
+    torch.cuda.synchronize()
+    shard = dict(embeds_1bp=emb.embeds_1bp, embeds_128bp=emb.embeds_128bp, embeds_pair=emb.embeds_pair,
+                 unet_output=tu.unet_output, single_repr=tu.single_repr, pairwise_repr=tu.pairwise_repr)
+    ncoll = eng.sp.n_collectives
+    gathered = {}
+    for k, v in shard.items():
+        v = v.contiguous()
+        if v.dim() == 4:  # pair rows [B, P_loc, P, C] -> gather along rows
+            Bq, Pl, Pn, C = v.shape
+            gathered[k] = eng.sp.gather_rows(v.view(Bq, Pl, Pn * C)).view(Bq, world * Pl, Pn, C)
+        else:
+            gathered[k] = eng.sp.gather_rows(v)
+    eng.sp = None
+    if rank == 0:
+        emb, tu = model.get_embeds(seq, org, return_unet_transformer_outputs=True)
+        torch.cuda.synchronize()
+        full = dict(embeds_1bp=emb.embeds_1bp, embeds_128bp=emb.embeds_128bp, embeds_pair=emb.embeds_pair,
+                    unet_output=tu.unet_output, single_repr=tu.single_repr, pairwise_repr=tu.pairwise_repr)
+        rep = {k: ((gathered[k] - full[k]).abs().max() / full[k].abs().max()).item() for k in full}
+        ok = all(v <= 1e-5 for v in rep.values())
+        print("SP_CHECK " + json.dumps(dict(ok=ok, world=world, L=L, B=B, collectives=ncoll, max_rel_diff=rep)), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
