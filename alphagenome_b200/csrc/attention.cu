@@ -9,10 +9,11 @@
 //           same pipeline as mode 0 with p = exp(logit - max).  Epilogue adds to_v's bias (softmax rows
 //           sum to 1, so the bias commutes with the weighted sum) and the residual, in fp32.
 //
-// One CTA per (batch, head, 128-query tile); 192 threads:
+// One CTA per (batch, head, 128-query tile); 320 threads:
 //   warp 0 (one lane)  TMA: Q once; per key block K [128 keys x 128] and V^T [dv x 128 keys], 2-stage rings
 //   warp 1 (one lane)  tcgen05.mma issuer: S ping-pong (2 x 128 TMEM columns), O (dv columns)
-//   warps 2-5          softmax: thread = query row; also the final O / rowsum epilogue
+//   warps 2-9          softmax: thread = query row, two warps per row quarter (one per 64-key half of a block);
+//                      also the final O / rowsum epilogue
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,7 +27,7 @@ constexpr int kAttQBytes = kAttBM * kAttD * 2;          // 32 KB (two 64-wide sw
 constexpr int kAttKBytes = kAttBN * kAttD * 2;          // 32 KB
 constexpr int kAttVBytesMax = kAttMaxDv * kAttBN * 2;   // 48 KB
 constexpr int kAttPBytes = kAttBM * kAttBN * 2;         // 32 KB
-constexpr int kAttThreads = 192;
+constexpr int kAttThreads = 320;
 constexpr int kAttSmem = 1024 + kAttQBytes + 2 * kAttKBytes + 2 * kAttVBytesMax + kAttPBytes + 256;
 
 struct AttnKParams {
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
       mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
     }
@@ -186,7 +187,12 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     __syncwarp();
   } else {
     // ---------------------------------------------------------------------------- softmax + epilogue
-    const int qd = warp & 3;                 // TMEM lane quarter
+    // 8 warps: TMEM lane quarter qd = warp & 3 (thread = query row), key half hf = (warp - 2) >> 2: the warp
+    // owns keys [64 hf, 64 hf + 64) of every 128-key block = one 128B-swizzled P atom column, so the two
+    // halves never touch the same smem or barrier and each SM sub-partition has two softmax warps to overlap
+    // MUFU latency.
+    const int qd = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int lrow = qd * 32 + lane;         // row within the tile
     const int row = q0 + lrow;               // query index
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
@@ -196,46 +202,62 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     const float sc_soft = a.scale / a.softcap;           // logits/softcap
     const float sc_exp = a.softcap * LOG2E;              // exp(softcap * tanh(.))
     const float sc_plain = a.scale * LOG2E;
+    const float inv_cap = 1.0f / a.softcap;
     const int brow = (row < a.n_q ? row : a.n_q - 1) / 16;
     const int brows = a.bias_rows > 0 ? a.bias_rows : a.bias_p;
     const float* bias_row = a.mode == 0 ? a.bias + (((long)b * a.heads + h) * brows + brow) * a.bias_p : nullptr;
-    uint8_t* prow = sP + lrow * 128;          // this row inside a swizzle atom-column
+    uint8_t* prow = sP + hf * (kAttPBytes / 2) + lrow * 128;   // this row inside this half's swizzle atom column
     const int sw = lrow & 7;
+    float* xch = reinterpret_cast<float*>(sP);   // [2][128] exchange between the halves (sP is idle at those points)
+    float mneg = 0.0f;
 
     for (int s = 0; s < nsteps; ++s) {
       const int st = s & 1;
       const int kb = s < npre ? s : s - npre;
-      const int key0 = kb * kAttBN;
+      const int key0 = kb * kAttBN + hf * 64;
+      if (s == npre && npre > 0) {
+        // mode 1: pass 1 done -> combine the two halves' row maxima before any exp (and before P is written)
+        xch[hf * 128 + lrow] = rowmax;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        rowmax = fmaxf(rowmax, xch[(hf ^ 1) * 128 + lrow]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mneg = -rowmax * sc_plain;
+      }
       mbar_wait(&s_full[st], (s >> 1) & 1, 0x170u + st, p.err);
       tc_fence_after();
-      const uint32_t s_addr = tmem_S + lane_off + (uint32_t)st * kAttBN;
+      const uint32_t s_addr = tmem_S + lane_off + (uint32_t)st * kAttBN + (uint32_t)hf * 64;
       if (s < npre) {
-        // pass 1 of mode 1: exact row max of the raw logits
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(s_addr + ch * 32, r);
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (key0 + ch * 32 + j < a.n_k) rowmax = fmaxf(rowmax, __uint_as_float(r[j]));
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t r[32];
+          tmem_ld_32x32(s_addr + c2 * 32, r);
+          tmem_ld_wait();
+          if (key0 + c2 * 32 + 32 <= a.n_k) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rowmax = fmaxf(rowmax, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (key0 + c2 * 32 + j < a.n_k) rowmax = fmaxf(rowmax, __uint_as_float(r[j]));
+          }
         }
       } else {
         const int f = s - npre;
-        const float mneg = a.mode == 1 ? -rowmax * sc_plain : 0.0f;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          // the two bias scalars (16 keys each) this 32-key chunk needs, pre-divided by the soft-cap
-          float bq0 = 0.0f, bq1 = 0.0f;
-          if (a.mode == 0) {
-            const int pc = kb * 8 + ch * 2;
-            if (pc < a.bias_p) bq0 = __ldg(bias_row + pc) * (1.0f / a.softcap);
-            if (pc + 1 < a.bias_p) bq1 = __ldg(bias_row + pc + 1) * (1.0f / a.softcap);
-          }
+        // the four bias scalars (16 keys each) of this half-block, pre-divided by the soft-cap
+        float bq[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.mode == 0) {
+          const int pc = kb * 8 + hf * 4;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (pc + t < a.bias_p) bq[t] = __ldg(bias_row + pc + t) * inv_cap;
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t r[32];
-          tmem_ld_32x32(s_addr + ch * 32, r);
+          tmem_ld_32x32(s_addr + c2 * 32, r);
           tmem_ld_wait();
-          if ((ch & 1) == 0) mbar_wait(&p_empty[ch >> 1], (f & 1) ^ 1u, 0x180u + (ch >> 1), p.err);
+          if (c2 == 0) mbar_wait(&p_empty[hf], (f & 1) ^ 1u, 0x180u + hf, p.err);
+          const bool full = key0 + c2 * 32 + 32 <= a.n_k;
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             float pv[8];
@@ -244,9 +266,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
               const int j = g8 * 8 + e;
               const float sv = __uint_as_float(r[j]);
               float pe;
-              if (a.mode == 0) pe = ex2_approx(tanh_approx(fmaf(sv, sc_soft, (j >> 4) ? bq1 : bq0)) * sc_exp);
+              if (a.mode == 0) pe = ex2_approx(tanh_approx(fmaf(sv, sc_soft, bq[c2 * 2 + (j >> 4)])) * sc_exp);
               else pe = ex2_approx(fmaf(sv, sc_plain, mneg));
-              if (key0 + ch * 32 + j >= a.n_k) pe = 0.0f;
+              if (!full && key0 + c2 * 32 + j >= a.n_k) pe = 0.0f;
               pv[e] = pe;
             }
             uint4 pk;
@@ -254,37 +276,36 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
             pk.y = pack_bf16x2(pv[2], pv[3]);
             pk.z = pack_bf16x2(pv[4], pv[5]);
             pk.w = pack_bf16x2(pv[6], pv[7]);
-            // the normaliser sums exactly what the tensor core will multiply (bf16-rounded weights)
-            {
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f2 = __bfloat1622float2(hh[e]);
-                rowsum += f2.x + f2.y;
-              }
-            }
-            const int chunk16 = (ch & 1) * 4 + g8;  // 16-byte chunk index inside the 64-key atom row
-            *reinterpret_cast<uint4*>(prow + (ch >> 1) * (kAttPBytes / 2) + ((chunk16 ^ sw) << 4)) = pk;
-          }
-          if (ch & 1) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[ch >> 1]);
+            // the normaliser sums exactly what the tensor core will multiply (bf16-rounded weights):
+            // a bf16 is the top half of an fp32, so unpacking is a shift / mask
+            rowsum += (__uint_as_float(pk.x << 16) + __uint_as_float(pk.x & 0xFFFF0000u)) +
+                      (__uint_as_float(pk.y << 16) + __uint_as_float(pk.y & 0xFFFF0000u)) +
+                      (__uint_as_float(pk.z << 16) + __uint_as_float(pk.z & 0xFFFF0000u)) +
+                      (__uint_as_float(pk.w << 16) + __uint_as_float(pk.w & 0xFFFF0000u));
+            const int chunk16 = c2 * 4 + g8;  // 16-byte chunk index inside the 64-key atom row
+            *reinterpret_cast<uint4*>(prow + ((chunk16 ^ sw) << 4)) = pk;
           }
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[hf]);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
     }
 
-    // ---- epilogue: O / rowsum (+ bias + residual) ----
+    // ---- epilogue: O / rowsum (+ bias + residual); each half writes dv/2 of the columns ----
     mbar_wait(o_full, 0, 0x190u, p.err);
     tc_fence_after();
+    xch[hf * 128 + lrow] = rowsum;            // all MMAs are complete: sP is free
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    rowsum += xch[(hf ^ 1) * 128 + lrow];
     const float inv = 1.0f / rowsum;
     const long obase = (long)b * a.out_bstride + (long)h * a.out_hstride + (long)row * a.out_ld;
+    const int cbeg = hf * (dv / 2), cend = cbeg + dv / 2;
 #pragma unroll 1
-    for (int c0 = 0; c0 < dv; c0 += 32) {
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_O + lane_off + (uint32_t)c0, r);
       tmem_ld_wait();
@@ -336,7 +357,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
 int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
   if (!a.Q || !a.K || !a.Vt || !a.out) return set_error("ag_attention_fwd: Q, K, Vt and out must be non-null");
   if (a.d != kAttD) return set_error("ag_attention_fwd: head dim %d unsupported (kernel is built for d=128)", a.d);
-  if (a.dv < 32 || a.dv > kAttMaxDv || a.dv % 32) return set_error("ag_attention_fwd: dv=%d must be a multiple of 32 in [32, 192]", a.dv);
+  if (a.dv < 64 || a.dv > kAttMaxDv || a.dv % 64) return set_error("ag_attention_fwd: dv=%d must be a multiple of 64 in [64, 192]", a.dv);
   if (a.batch < 1 || a.heads < 1 || a.n_q < 1 || a.n_k < 1) return set_error("ag_attention_fwd: bad sizes");
   if (a.kv_heads != 1 && a.kv_heads != a.heads) return set_error("ag_attention_fwd: kv_heads must be 1 (MQA) or == heads");
   if (a.mode != 0 && a.mode != 1) return set_error("ag_attention_fwd: mode must be 0 (softcap+bias) or 1 (plain softmax)");

@@ -53,3 +53,15 @@ ay = torch.empty(1, M, C, **bf)
 timeit(lambda: ops.gemm(skipact, W1, pre_shift=bias, res=low, res_shift=1, out=y, actA=Act(ay, s, t, ACT_GELU1702)), "w1_upres", 2.0 * M * C * C)
 # (4) conv5 768->768 res + out + actA (UpresBlock.conv_out)
 timeit(lambda: ops.gemm(ay, W5, pre_shift=bias, res=y, out=x0, actA=Act(a0, s, t, ACT_GELU1702)), "conv5_out", 2.0 * M * C * C * 5)
+# (5) outembed_1bp: 768 -> 1536, residual at row>>7, fp32 output with accurate GELU1702 (OutputEmbedding)
+W2 = (torch.randn(1, 2 * C, C, **f32) * 0.05).to(torch.bfloat16)
+skp = torch.randn(1, M // 128, 2 * C, **f32)
+s2, t2 = torch.rand(2 * C, **f32) + 0.5, torch.randn(1, 2 * C, **f32)
+e1 = torch.empty(1, M, 2 * C, **f32)
+b2 = torch.randn(2 * C, **f32)
+timeit(lambda: ops.gemm(a0, W2, pre_shift=b2, res=skp, res_shift=7, actA=Act(e1, s2, t2, ACT_GELU1702)), "outembed_1bp", 2.0 * M * C * 2 * C)
+# (6) pair linear K=128 -> 256, bf16 out (PairwiseRowAttention.to_qk)
+pa = torch.randn(1, M, 128, **f32).to(torch.bfloat16)
+Wp = (torch.randn(1, 256, 128, **f32) * 0.1).to(torch.bfloat16)
+qk = torch.empty(1, M, 256, **bf)
+timeit(lambda: ops.gemm(pa, Wp, actA=Act(qk)), "pair_k128", 2.0 * M * 128 * 256)
