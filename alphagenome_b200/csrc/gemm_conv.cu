@@ -4,16 +4,18 @@
 // DNAEmbed.pointwise AG:1163, DownresBlock AG:470-481, UpresBlock AG:503-519, and the nn.Linear layers of
 // Attention / FeedForward / SingleToPairwise / PairwiseRowAttention / OutputEmbedding.
 //
-// Design (one persistent CTA per SM, 320 threads):
+// Design (one persistent CTA per SM, 576 threads):
 //   warp 0 (one lane)  TMA producer: per (tap, 64-wide K block) one A box [128 rows x 64] at row offset
 //                      tap - taps/2 (out-of-range rows are zero-filled by TMA = the conv's zero padding)
 //                      and one W box [n_tile x 64], both 128B-swizzled, into a 4-stage smem ring.
 //   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (M=128, N=n_tile, K=16) per stage, fp32 accumulators in
 //                      TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps the
 //                      mainloop of tile i+1.
-//   warps 2-9          epilogue: tcgen05.ld 32x16 blocks -> padded smem -> each lane owns 4 consecutive channels
-//                      of 4 rows -> fused affine / ReLU / residual / scale / activation / maxpool2 ->
-//                      128-bit global loads and stores.
+//   warps 2-17         epilogue (4 warps per TMEM lane quarter, each takes every 4th 16-column chunk):
+//                      tcgen05.ld 32x16 -> XOR-swizzled smem -> each lane owns 4 consecutive channels of 4 rows ->
+//                      fused affine / ReLU / residual / scale / activation / maxpool2 -> 128-bit global accesses.
+//                      The kernel is instantiated per set of enabled outputs (template FLAGS) so disabled paths
+//                      cost no instructions; all pointer arithmetic is hoisted to one 64-bit base per tile.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,12 +27,14 @@ constexpr int kStages = 4;
 constexpr int kMaxNTile = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kBBytesMax = kMaxNTile * kBlockK * 2; // 32 KB
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiCols = 16;                          // columns per TMEM load / staged chunk
-constexpr int kEpiStride = 20;                        // floats per staged row (16 + 4 pad; 5 x 16 B, odd)
-constexpr int kEpiBytes = kEpiWarps * 32 * kEpiStride * 4;
+constexpr int kEpiBytesPerWarp = 32 * kEpiCols * 4;   // 2 KB, XOR-swizzled (no padding)
+constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int kGemmSmem = 1024 /*align slack*/ + kStages * (kABytes + kBBytesMax) + kEpiBytes + 256;
+
+enum : int { F_RES = 1, F_OUT = 2, F_ACTA = 4, F_ACTB = 8, F_POOL = 16, F_COUNT = 32 };
 
 struct GemmKParams {
   CUtensorMap tmA;
@@ -40,22 +44,23 @@ struct GemmKParams {
   unsigned int* err;
 };
 
-// One activated output for 4 consecutive channels of one row (scale/shift pre-loaded per chunk).
-// Only ACT_NONE / ACT_GELU1702 occur in GEMM epilogues (checked on the host): one uniform branch per 4 elements.
+// Only ACT_NONE / ACT_GELU1702 occur in GEMM epilogues (checked on the host).
 __device__ __forceinline__ float gelu1702_fast(float x) {   // 0.5x + 0.5x*tanh(0.851x): one MUFU op
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx(0.851f * x), hx);
 }
 __device__ __forceinline__ float gelu1702_acc(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 
-__device__ __forceinline__ void epi_store4(const AgEpiOut& o, long off, float4 v, const float4& s, const float4& t) {
+// One activated output for 4 consecutive channels of one row: dst = act(v*s + t), bf16 (fast GELU) or fp32.
+__device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool is_bf16, bool gelu, float4 v,
+                                           const float4& s, const float4& t) {
   float4 y;
   y.x = fmaf(v.x, s.x, t.x);
   y.y = fmaf(v.y, s.y, t.y);
   y.z = fmaf(v.z, s.z, t.z);
   y.w = fmaf(v.w, s.w, t.w);
-  if (o.dtype == 0) {
-    if (o.act != ACT_NONE) {
+  if (is_bf16) {
+    if (gelu) {
       y.x = gelu1702_fast(y.x);
       y.y = gelu1702_fast(y.y);
       y.z = gelu1702_fast(y.z);
@@ -66,23 +71,24 @@ __device__ __forceinline__ void epi_store4(const AgEpiOut& o, long off, float4 v
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&lo);
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(o.ptr) + off) = pk;
+    *reinterpret_cast<uint2*>(base + (size_t)elem_off * 2) = pk;
   } else {
-    if (o.act != ACT_NONE) {
+    if (gelu) {
       y.x = gelu1702_acc(y.x);
       y.y = gelu1702_acc(y.y);
       y.z = gelu1702_acc(y.z);
       y.w = gelu1702_acc(y.w);
     }
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.ptr) + off) = y;
+    *reinterpret_cast<float4*>(base + (size_t)elem_off * 4) = y;
   }
 }
 
-__device__ __forceinline__ float4 ldg4_or(const float* p, long off, float dflt) {
-  if (p) return __ldg(reinterpret_cast<const float4*>(p + off));
+__device__ __forceinline__ float4 ldg4_or(const float* p, float dflt) {
+  if (p) return __ldg(reinterpret_cast<const float4*>(p));
   return make_float4(dflt, dflt, dflt, dflt);
 }
 
+template <int FLAGS>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
 
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kABytes;
-  float* sEpi = reinterpret_cast<float*>(smem + kStages * (kABytes + kBBytesMax));
+  uint8_t* sEpi = smem + kStages * (kABytes + kBBytesMax);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytesMax) + kEpiBytes);
   uint64_t* full_bar = bars;                 // [kStages]
   uint64_t* empty_bar = bars + kStages;      // [kStages]
@@ -182,19 +188,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
-    // Two warps per TMEM lane quarter; each takes every other 16-column chunk.  Per chunk: LDTM (thread =
-    // row) -> padded smem -> each lane re-reads 4 consecutive channels of 4 rows (two adjacent-row pairs, so
-    // maxpool2 is thread-local) -> 128-bit global loads/stores.
+    // ------------------------------------------------------------------ epilogue (warps 2..17)
+    // Four warps per TMEM lane quarter (q = warp & 3); warp slot = (warp-2)>>2 takes chunks ch = slot, slot+4, ...
+    // Per chunk: residual rows requested from global first, then LDTM (thread = row) -> swizzled smem -> each
+    // lane re-reads 4 consecutive channels of 4 rows (two adjacent-row pairs, so maxpool2 is thread-local).
+    constexpr bool kRes = (FLAGS & F_RES) != 0, kOut = (FLAGS & F_OUT) != 0, kActA = (FLAGS & F_ACTA) != 0,
+                   kActB = (FLAGS & F_ACTB) != 0, kPool = (FLAGS & F_POOL) != 0;
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    float* stg = sEpi + (warp - 2) * 32 * kEpiStride;
+    const int slot = (warp - 2) >> 2;
+    uint8_t* stg = sEpi + (warp - 2) * kEpiBytesPerWarp;
     const int cg = lane & 3;     // channel group: columns 4cg..4cg+3 of the chunk
     const int rsel = lane >> 2;  // rows 2*rsel + {0,1} (+16)
+    // staging addresses: 64 B rows, two rows per 128 B line, 16 B unit index XOR (line & 7)
+    const uint32_t st_line = (uint32_t)(lane >> 1), st_u0 = (uint32_t)(lane & 1) * 4;
+    uint8_t* st_wr = stg + st_line * 128;
+    const uint32_t st_x = st_line & 7;
     int as = 0;
     uint32_t aphase = 0;
     const float post = g.post_scale ? __ldg(g.post_scale) : 1.0f;
-    const bool do_pool = (g.pool != nullptr) || (g.actP.ptr != nullptr);
+    const bool relu = g.relu != 0;
+    const bool a16 = g.actA.dtype == 0, aG = g.actA.act != ACT_NONE;
+    const bool b16 = g.actB.dtype == 0, bG = g.actB.act != ACT_NONE;
+    const bool p16 = g.actP.dtype == 0, pG = g.actP.act != ACT_NONE;
+    const bool has_poolf = kPool && g.pool != nullptr, has_actP = kPool && g.actP.ptr != nullptr;
     const int nchunks = p.n_tile / kEpiCols;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
@@ -202,79 +218,98 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const int mt = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
       const int n0 = nt * p.n_tile;
-      const int r_base = mt * kBlockM + q * 32;
+      const int row_t = mt * kBlockM;              // first row of the tile
+      const int lr_base = q * 32;                  // this warp's rows inside the tile
+      // one 64-bit base per tensor per tile; everything below is 32-bit in-tile offsets
+      const float* res_t = kRes ? g.res + (long)b * g.res_bstride + (long)(row_t >> g.res_shift) * g.res_ld + n0 : nullptr;
+      char* out_t = kOut ? reinterpret_cast<char*>(g.out + (long)b * g.out_bstride + (long)row_t * g.out_ld + n0) : nullptr;
+      char* actA_t = kActA ? reinterpret_cast<char*>(g.actA.ptr) + ((long)b * g.actA.bstride + (long)row_t * g.actA.ld + n0) * (a16 ? 2 : 4) : nullptr;
+      char* actB_t = kActB ? reinterpret_cast<char*>(g.actB.ptr) + ((long)b * g.actB.bstride + (long)row_t * g.actB.ld + n0) * (b16 ? 2 : 4) : nullptr;
+      char* pool_t = has_poolf ? reinterpret_cast<char*>(g.pool + (long)b * g.pool_bstride + (long)(row_t >> 1) * g.pool_ld + n0) : nullptr;
+      char* actP_t = has_actP ? reinterpret_cast<char*>(g.actP.ptr) + ((long)b * g.actP.bstride + (long)(row_t >> 1) * g.actP.ld + n0) * (p16 ? 2 : 4) : nullptr;
+      const float* ps_t = g.pre_scale ? g.pre_scale + n0 : nullptr;
+      const float* pt_t = g.pre_shift ? g.pre_shift + n0 : nullptr;
+      const float* sA_t = (kActA && g.actA.scale) ? g.actA.scale + n0 : nullptr;
+      const float* tA_t = (kActA && g.actA.shift) ? g.actA.shift + (long)b * g.actA.shift_bstride + n0 : nullptr;
+      const float* sB_t = (kActB && g.actB.scale) ? g.actB.scale + n0 : nullptr;
+      const float* tB_t = (kActB && g.actB.shift) ? g.actB.shift + (long)b * g.actB.shift_bstride + n0 : nullptr;
+      const float* sP_t = (has_actP && g.actP.scale) ? g.actP.scale + n0 : nullptr;
+      const float* tP_t = (has_actP && g.actP.shift) ? g.actP.shift + (long)b * g.actP.shift_bstride + n0 : nullptr;
+      const int res_cols = kRes ? g.res_ch - n0 : 0;   // residual applies to in-tile columns < res_cols
+      const int rows_left = g.M - row_t;               // in-tile rows >= rows_left do not exist
 
       mbar_wait(&tfull_bar[as], aphase, 0x40u + as, p.err);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kMaxNTile;
+      const uint32_t t_addr = tmem_base + ((uint32_t)lr_base << 16) + (uint32_t)as * kMaxNTile;
 
-      for (int ch = half; ch < nchunks; ch += 2) {
-        const int c = n0 + ch * kEpiCols + 4 * cg;
-        // ---- global loads first: residual rows and per-channel parameters are in flight while the
-        //      accumulators travel TMEM -> registers -> smem ----
-        const bool has_res = (g.res != nullptr) && (c < g.res_ch);
+      for (int ch = slot; ch < nchunks; ch += 4) {
+        const int col = ch * kEpiCols + 4 * cg;  // in-tile column of this lane's 4 channels
+        // ---- residual rows first: in flight while the accumulators travel TMEM -> registers -> smem ----
         float4 rr[4];
+        if constexpr (kRes) {
+          const bool on = col < res_cols;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = r_base + 2 * rsel + (k & 1) + 16 * (k >> 1);
-          rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res && row < g.M)
-            rr[k] = __ldg(reinterpret_cast<const float4*>(g.res + (long)b * g.res_bstride + (long)(row >> g.res_shift) * g.res_ld + c));
+          for (int k = 0; k < 4; ++k) {
+            const int lr = lr_base + 2 * rsel + ((k & 1) ^ (rsel & 1)) + 16 * (k >> 1);
+            rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on && lr < rows_left)
+              rr[k] = __ldg(reinterpret_cast<const float4*>(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col)));
+          }
         }
-        const float4 ps = ldg4_or(g.pre_scale, c, 1.0f);
-        const float4 pt = ldg4_or(g.pre_shift, c, 0.0f);
-        float4 sA, tA, sB, tB, sP, tP;
-        if (g.actA.ptr) { sA = ldg4_or(g.actA.scale, c, 1.0f); tA = ldg4_or(g.actA.shift, (long)b * g.actA.shift_bstride + c, 0.0f); }
-        if (g.actB.ptr) { sB = ldg4_or(g.actB.scale, c, 1.0f); tB = ldg4_or(g.actB.shift, (long)b * g.actB.shift_bstride + c, 0.0f); }
-        if (g.actP.ptr) { sP = ldg4_or(g.actP.scale, c, 1.0f); tP = ldg4_or(g.actP.shift, (long)b * g.actP.shift_bstride + c, 0.0f); }
-
         uint32_t r[16];
         tmem_ld_32x16(t_addr + (uint32_t)(ch * kEpiCols), r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * kEpiStride + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          *reinterpret_cast<uint4*>(st_wr + (((st_u0 + j) ^ st_x) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        // per-channel parameters (L1-resident after the first tile)
+        const float4 ps = ldg4_or(ps_t ? ps_t + col : nullptr, 1.0f);
+        const float4 pt = ldg4_or(pt_t ? pt_t + col : nullptr, 0.0f);
+        float4 sA, tA, sB, tB, sP, tP;
+        if constexpr (kActA) { sA = ldg4_or(sA_t ? sA_t + col : nullptr, 1.0f); tA = ldg4_or(tA_t ? tA_t + col : nullptr, 0.0f); }
+        if constexpr (kActB) { sB = ldg4_or(sB_t ? sB_t + col : nullptr, 1.0f); tB = ldg4_or(tB_t ? tB_t + col : nullptr, 0.0f); }
+        if (has_actP) { sP = ldg4_or(sP_t ? sP_t + col : nullptr, 1.0f); tP = ldg4_or(tP_t ? tP_t + col : nullptr, 0.0f); }
         __syncwarp();
 
-        const long out_base = (long)b * g.out_bstride + c;
-        const long a_base = (long)b * g.actA.bstride + c;
-        const long b_base = (long)b * g.actB.bstride + c;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float4 v[2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int lr = 2 * rsel + h + 16 * i;
-            const int row = r_base + lr;
-            float4 x = *reinterpret_cast<const float4*>(stg + lr * kEpiStride + 4 * cg);
-            const float4 ra = rr[i * 2 + h];
+          for (int stp = 0; stp < 2; ++stp) {
+            // odd row-selectors take their odd row first: the two rows a quarter-warp reads in one LDS.128 then
+            // differ in parity and hit disjoint bank groups of the swizzled staging tile
+            const int wr = 2 * rsel + (stp ^ (rsel & 1)) + 16 * i;   // row inside this warp's 32
+            const int lr = lr_base + wr;                              // row inside the tile
+            const uint32_t line = (uint32_t)(wr >> 1);
+            float4 x = *reinterpret_cast<const float4*>(stg + line * 128 + ((((uint32_t)(wr & 1) * 4 + cg) ^ (line & 7)) << 4));
             x.x = fmaf(x.x, ps.x, pt.x);
             x.y = fmaf(x.y, ps.y, pt.y);
             x.z = fmaf(x.z, ps.z, pt.z);
             x.w = fmaf(x.w, ps.w, pt.w);
-            if (g.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            x.x = (x.x + ra.x) * post;
-            x.y = (x.y + ra.y) * post;
-            x.z = (x.z + ra.z) * post;
-            x.w = (x.w + ra.w) * post;
-            if (row < g.M) {
-              if (g.out) *reinterpret_cast<float4*>(g.out + out_base + (long)row * g.out_ld) = x;
-              if (g.actA.ptr) epi_store4(g.actA, a_base + (long)row * g.actA.ld, x, sA, tA);
-              if (g.actB.ptr) epi_store4(g.actB, b_base + (long)row * g.actB.ld, x, sB, tB);
+            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if constexpr (kRes) {
+              const float4 ra = rr[i * 2 + stp];
+              x.x += ra.x; x.y += ra.y; x.z += ra.z; x.w += ra.w;
             }
-            v[h] = x;
+            x.x *= post; x.y *= post; x.z *= post; x.w *= post;
+            if (lr < rows_left) {
+              if constexpr (kOut) *reinterpret_cast<float4*>(out_t + (size_t)(uint32_t)(lr * g.out_ld + col) * 4) = x;
+              if constexpr (kActA) epi_store4(actA_t, (uint32_t)(lr * g.actA.ld + col), a16, aG, x, sA, tA);
+              if constexpr (kActB) epi_store4(actB_t, (uint32_t)(lr * g.actB.ld + col), b16, bG, x, sB, tB);
+            }
+            v[stp] = x;
           }
-          if (do_pool) {
-            const int row = r_base + 2 * rsel + 16 * i;
-            if (row + 1 < g.M) {
+          if constexpr (kPool) {
+            const int lr = lr_base + 2 * rsel + 16 * i;   // even row of the pair
+            if (lr + 1 < rows_left) {
               float4 pv;
               pv.x = fmaxf(v[0].x, v[1].x);
               pv.y = fmaxf(v[0].y, v[1].y);
               pv.z = fmaxf(v[0].z, v[1].z);
               pv.w = fmaxf(v[0].w, v[1].w);
-              const long prow = row >> 1;
-              if (g.pool) *reinterpret_cast<float4*>(g.pool + (long)b * g.pool_bstride + prow * g.pool_ld + c) = pv;
-              if (g.actP.ptr) epi_store4(g.actP, (long)b * g.actP.bstride + prow * g.actP.ld + c, pv, sP, tP);
+              const int pr = lr >> 1;
+              if (has_poolf) *reinterpret_cast<float4*>(pool_t + (size_t)(uint32_t)(pr * g.pool_ld + col) * 4) = pv;
+              if (has_actP) epi_store4(actP_t, (uint32_t)(pr * g.actP.ld + col), p16, pG, pv, sP, tP);
             }
           }
         }
@@ -298,6 +333,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
 // ----------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------
+typedef void (*GemmKernelFn)(const GemmKParams);
+
+// one instantiation per set of enabled outputs (res / out / actA / actB / pool)
+template <int... I>
+struct GemmTable {
+  GemmKernelFn fn[sizeof...(I)] = {gemm_conv_kernel<I>...};
+};
+template <int N, int... I>
+struct MakeGemmTable : MakeGemmTable<N - 1, N - 1, I...> {};
+template <int... I>
+struct MakeGemmTable<0, I...> {
+  typedef GemmTable<I...> type;
+};
+static const MakeGemmTable<F_COUNT>::type kGemmTable;
+
 static int pick_n_tile(int N) {
   for (int t = 256; t >= 16; t -= 16)
     if (N % t == 0) return t;
@@ -359,14 +409,18 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
     if (int rc = make_tensor_map_bf16(&p.tmB, a.W, 3, dims, strides, box)) return rc;
   }
 
-  static thread_local int attr_set_for = -1;
-  if (attr_set_for != device) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+  const int flags = (a.res ? F_RES : 0) | (a.out ? F_OUT : 0) | (a.actA.ptr ? F_ACTA : 0) | (a.actB.ptr ? F_ACTB : 0) |
+                    ((a.pool || a.actP.ptr) ? F_POOL : 0);
+  if (flags == 0) return set_error("ag_gemm_fwd: no output requested");
+  GemmKernelFn fn = kGemmTable.fn[flags];
+  static thread_local unsigned char attr_done[64][F_COUNT];
+  if (!attr_done[device][flags]) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
     if (e != cudaSuccess) return set_error("ag_gemm_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set_for = device;
+    attr_done[device][flags] = 1;
   }
   int grid = p.total_tiles < sm_count(device) ? p.total_tiles : sm_count(device);
-  gemm_conv_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(p);
+  fn<<<grid, kGemmThreads, kGemmSmem, stream>>>(p);
   return check_launch("ag_gemm_fwd");
 }
 

@@ -322,6 +322,13 @@ class AlphaGenome(nn.Module):
         self.dim_128bp = 2 * last_dim
         self.dim_contacts = self.transformer_unet.transformer.dim_pairwise
         self.heads = nn.ModuleDict()
+        self.cuda_graphs = False  # see enable_cuda_graphs()
+
+    def enable_cuda_graphs(self, enabled: bool = True):
+        """Replay the forward from a CUDA graph (per input shape).  Outputs are then static buffers that the next
+        call with the same shape overwrites — copy them if you need to keep them."""
+        self.cuda_graphs = bool(enabled)
+        return self
 
     @property
     def total_parameters(self):
@@ -338,7 +345,8 @@ class AlphaGenome(nn.Module):
         from .trunk import engine_for
 
         organism_index = self._organism_tensor(seq, organism_index)
-        out = engine_for(self.transformer_unet, self).run_embeds(seq, organism_index)
+        eng = engine_for(self.transformer_unet, self)
+        out = eng.run_embeds_graphed(seq, organism_index) if self.cuda_graphs else eng.run_embeds(seq, organism_index)
         embeds = Embeds(out["embeds_1bp"], out["embeds_128bp"], out["embeds_pair"])
         if not return_unet_transformer_outputs:
             return embeds

@@ -52,6 +52,7 @@ class TrunkEngine:
         self._rel: Dict = {}
         self.collect = None  # optional callback(name, tensor) for per-stage parity tests
         self.sp = None       # alphagenome_b200.parallel.SeqParallel when the context is sharded over ranks
+        self._graphs: Dict = {}
 
     # ------------------------------------------------------------------------------------------ packing
     def _version_key(self, device):
@@ -68,7 +69,7 @@ class TrunkEngine:
         if self._pack is not None and self._pack_key == key:
             return self._pack
         unet = self.unet()
-        if device.type != "cuda":
+        if device.type != "cuda" and not getattr(self, "_allow_cpu_pack", False):  # (tests pack on CPU to compare layouts)
             raise ops._lib.AgbError("alphagenome_b200 runs only on a CUDA (sm_100a) device; move the model and inputs to cuda")
         f32 = dict(device=device, dtype=torch.float32)
 
@@ -443,6 +444,35 @@ class TrunkEngine:
             pairT = self.sp.transpose_blocks(pair) if sharded else None  # symmetrize needs pair[j, i] (AG:1253)
             ops.pair_out_embed(pair, op["w"], op["b"], op["emb"].index_select(0, organism_index).contiguous(), epair, pairT=pairT)
             out.update(embeds_1bp=e1, embeds_128bp=e128, embeds_pair=epair)
+        return out
+
+    def run_embeds_graphed(self, seq, organism_index):
+        """Same as run_embeds, replayed from a CUDA graph (one per input shape): removes the ~190 per-launch host
+        round trips, which matter once a rank's share of the forward is only a few ms.  The returned tensors are
+        the graph's static outputs — they are overwritten by the next call with the same shape."""
+        key = (tuple(seq.shape), str(seq.device), self.sp is not None, self._version_key(seq.device))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if self.collect is not None:
+                raise ops._lib.AgbError("stage collection is not available under CUDA graphs")
+            s_seq = seq.to(torch.int64).clone()
+            s_org = organism_index.to(seq.device).long().clone()
+            stream = torch.cuda.Stream(device=seq.device)
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                self.run_embeds(s_seq, s_org)  # warm-up on the side stream: builds the pack / rope / rel caches
+            torch.cuda.current_stream().wait_stream(stream)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.run_embeds(s_seq, s_org)
+            self._graphs.clear()  # one shape at a time keeps the private pool bounded
+            ent = (g, s_seq, s_org, out)
+            self._graphs[key] = ent
+        g, s_seq, s_org, out = ent
+        s_seq.copy_(seq, non_blocking=True)
+        s_org.copy_(organism_index, non_blocking=True)
+        g.replay()
         return out
 
     def run_trunk(self, seq, pre_attend_embed=None):

@@ -75,3 +75,53 @@ def test_synthetic_weights_are_deterministic_and_perturbed():
     sd = synth_state_dict({"x.gamma": (8,), "x.beta": (8,), "y.weight": (4, 16), "rotary_emb.inv_freq": (64,)})
     assert "rotary_emb.inv_freq" not in sd  # formula buffer, never randomised
     assert abs(float(sd["x.gamma"].mean()) - 1) < 0.2 and float(sd["y.weight"].abs().max()) <= 0.25
+
+
+@pytest.mark.skipif(not Path("/root/reference/alphagenome_pytorch").exists(), reason="reference checkout not present (GPU box)")
+def test_install_on_the_real_reference_model_packs_identically():
+    """install() must find every parameter it needs on an unmodified reference AlphaGenome: pack both the
+    reference model and our mirror (same state_dict) on CPU and compare every packed tensor bit for bit."""
+    import sys
+
+    sys.path.insert(0, str(ROOT / "oracle" / "shims"))
+    sys.path.append("/root/reference")
+    from alphagenome_pytorch.alphagenome import AlphaGenome as RefAlphaGenome
+
+    import alphagenome_b200
+    from alphagenome_b200.init_weights import apply_synth_weights
+    from alphagenome_b200.trunk import engine_for
+
+    kw = dict(dims=(128, 256, 384), transformer_kwargs=dict(depth=2))
+    ref = RefAlphaGenome(**kw)
+    apply_synth_weights(ref, seed=5)
+    mine = alphagenome_b200.AlphaGenome(**kw)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    alphagenome_b200.install(ref)
+    packs = []
+    for m in (ref, mine):
+        eng = engine_for(m.transformer_unet, m)
+        eng._allow_cpu_pack = True
+        packs.append(eng.pack(torch.device("cpu")))
+
+    def flat(x, prefix=""):
+        if isinstance(x, dict):
+            for k, v in x.items():
+                yield from flat(v, f"{prefix}.{k}")
+        elif isinstance(x, (list, tuple)):
+            for i, v in enumerate(x):
+                yield from flat(v, f"{prefix}[{i}]")
+        else:
+            yield prefix, x
+
+    a, b = dict(flat(packs[0])), dict(flat(packs[1]))
+    assert a.keys() == b.keys() and len(a) > 100
+    for k in a:
+        if torch.is_tensor(a[k]):
+            assert torch.equal(a[k], b[k]), k
+        else:
+            assert a[k] == b[k], k
+    feats = ref.transformer_unet.transformer.rel_pos_features.features(8)
+    assert torch.equal(feats, mine.transformer_unet.transformer.rel_pos_features.features(8))
+    # and the reference's own RelativePosFeatures.forward agrees with ours (AG:587-604)
+    want = ref.transformer_unet.transformer.rel_pos_features(torch.zeros(1, 8 * 16, 4))
+    assert torch.equal(feats, want)
