@@ -127,9 +127,12 @@ def run_reference_arm(args):
 
 
 def workload_config(L, gpus):
-    return dict(workload=f"AlphaGenome() trunk forward (conv encoder + 9-layer tower with pair blocks + conv decoder + output embeddings), "
-                         f"B=1 x {L} bp per GPU, synthetic weights (default 7-stage dims 768..1536), no heads",
-                length_bp=L, batch_per_gpu=1, parallelism=f"dp{gpus} (independent sequence per GPU, no data-path collective)",
+    par = ("single GPU" if gpus == 1 else
+           f"sp{gpus}: ONE {L} bp context sharded along the sequence over {gpus} GPUs (2048 bp recomputed conv halos, "
+           f"K/V + pooled-row all-gathers and one pair all-to-all over NCCL/NVLink)")
+    return dict(workload="AlphaGenome() trunk forward (conv encoder + 9-layer tower with pair blocks + conv decoder + output "
+                         f"embeddings), B=1 x {L} bp, synthetic weights (default 7-stage dims 768..1536), no heads",
+                length_bp=L, global_batch=1, parallelism=par,
                 l2="per-step inputs+activations >> 126 MB L2 (1bp activations are GBs); no explicit flush needed")
 
 
@@ -142,6 +145,7 @@ def main():
     ap.add_argument("--length", type=int, default=FULL_L)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -166,8 +170,16 @@ def main():
     from alphagenome_b200.model import AlphaGenome
 
     _lib.check(_lib.load().ag_check_device(local_rank))
+    from alphagenome_b200.trunk import engine_for
+
     model = AlphaGenome().to(dev).eval()
     apply_synth_weights(model, seed=0)
+    eng = engine_for(model.transformer_unet, model)
+    if world > 1:
+        from alphagenome_b200.parallel import SeqParallel
+
+        eng.sp = SeqParallel()  # strong scaling: the same 1 Mbp context, sharded along the sequence
+    model.enable_cuda_graphs(not args.no_graph)
     L, B = args.length, 1
     tok_host = synth_tokens(B, L).pin_memory()
     org_host = torch.zeros(B, dtype=torch.long).pin_memory()
@@ -190,7 +202,7 @@ def main():
         t = tok_host.to(dev, non_blocking=True)
         o = org_host.to(dev, non_blocking=True)
         emb = model(t, o)
-        # result read-back into pinned host buffers: the whole 128 bp embedding and the pair embedding (the 1 bp
+        # result read-back into pinned host buffers: this rank's 128 bp embedding and pair embedding (the 1 bp
         # embedding stays on the device for downstream heads, as in the reference's get_embeds -> heads flow)
         outs = []
         for name, src in (("e128", emb.embeds_128bp), ("pair", emb.embeds_pair)):
@@ -206,7 +218,6 @@ def main():
     barrier()
 
     # --- timed: device-resident inputs ---
-    ops.PROFILE_GEMM = []
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -218,14 +229,8 @@ def main():
         step_resident()
     e1.record()
     barrier()
-    launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
-    prof = ops.PROFILE_GEMM
-    ops.PROFILE_GEMM = None
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    gemm_flops = sum(f for _, _, f in prof)
-    n_gemm = len(prof)
 
     # --- timed: end to end through the public API with host buffers ---
     out = step_e2e()
@@ -238,37 +243,70 @@ def main():
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1) / args.steps
-    h2d = tok_host.numel() * 8 + org_host.numel() * 8
-    d2h = sum(t.numel() * t.element_size() for t in out)
+    h2d = (tok_host.numel() * 8 + org_host.numel() * 8) * world
+    d2h = sum(t.numel() * t.element_size() for t in out) * world
 
-    tms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    # --- dominant-kernel timing: K more steps launched eagerly with a CUDA-event pair around every ag_gemm_fwd
+    #     (events cannot be recorded inside a graph replay); also counts our kernel launches per step ---
+    model.enable_cuda_graphs(False)
+    step_resident()
+    barrier()
+    ops.PROFILE_GEMM = []
+    launches0 = _lib.launch_count()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        step_resident()
+    p1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms_eager = p0.elapsed_time(p1) / args.steps
+    prof = ops.PROFILE_GEMM
+    ops.PROFILE_GEMM = None
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    gemm_flops = sum(f for _, _, f in prof)
+    n_gemm = len(prof)
+
+    tms = torch.tensor([ms, ms_e2e, ms_eager], device=dev, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
 
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = tms.tolist()
+    ms, ms_e2e, ms_eager = tms.tolist()
     if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
         return
     pk = peaks()
-    value = world * B * L / (ms * 1e-3)
-    e2e = world * B * L / (ms_e2e * 1e-3)
+    value = B * L / (ms * 1e-3)            # whole job: one context over all `world` GPUs
+    e2e = B * L / (ms_e2e * 1e-3)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 operands / fp32 accumulate + fp32 residual stream",
+                higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None,
+                dtype="bf16 operands / fp32 accumulate + fp32 residual stream",
                 data="synthetic", config=workload_config(L, world),
                 e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                gpu_launches=int(launches), clocks=clocks,
-                roofline=dict(kernel="gemm_conv_kernel (tcgen05 implicit-GEMM conv/linear)", bound="tensor", achieved=achieved,
+                gpu_launches=int(launches), launch_mode="cuda-graph replay" if not args.no_graph else "eager",
+                clocks=clocks,
+                roofline=dict(kernel="gemm_conv_kernel (tcgen05 implicit-GEMM conv/linear), rank 0", bound="tensor", achieved=achieved,
                               peak=pk["tf_sustained"], unit="TFLOP/s", frac=(achieved / pk["tf_sustained"]) if achieved else None,
                               traffic=None, peak_source=pk["src"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
-                              launches_per_step=n_gemm // max(args.steps, 1), share_of_step=gemm_ms / (ms * args.steps),
-                              algorithmic_tflop_per_step=gemm_flops / max(args.steps, 1) / 1e12))
-    if not args.no_cpu_baseline:
+                              launches_per_step=n_gemm // max(args.steps, 1), share_of_step=gemm_ms / (ms_eager * args.steps),
+                              algorithmic_tflop_per_step=gemm_flops / max(args.steps, 1) / 1e12,
+                              measured="CUDA events around every launch in %d eagerly launched steps (%.2f ms/step) right after the timed region" % (args.steps, ms_eager)))
+    if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         bps, secs = cpu_oracle_bps(CPU_SAMPLE_L, cores)
         line["cpu_baseline"] = dict(value=bps, unit=UNIT, cores=cores, kind="port", seconds=secs,
                                     sample=f"one forward of B=1 x {CPU_SAMPLE_L} bp (1/8 of the workload) through the pinned CPU oracle, fp32")
     print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
