@@ -1,4 +1,5 @@
 """Three representative ag_gemm_fwd launches with their real epilogues (for `ncu --set full -k regex:gemm_conv`)."""
+import os
 import sys
 from pathlib import Path
 
@@ -18,7 +19,15 @@ s, t = torch.rand(C, **f32) + 0.5, torch.randn(C, **f32)
 bias = torch.randn(C, **f32)
 
 
+ONCE = os.environ.get("PROBE_ONCE") == "1"   # one launch per case (for an ncu --set full capture)
+
+
 def timeit(fn, name, flops):
+    if ONCE:
+        fn()
+        torch.cuda.synchronize()
+        print(f"{name}: launched once", flush=True)
+        return
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
