@@ -112,6 +112,7 @@ EXPORTED = [
     "ag_launch_count",
     "ag_check_device",
     "ag_watchdog_status",
+    "ag_gemm_set_cta_group",
     "ag_gemm_fwd",
     "ag_attention_fwd",
     "ag_onehot_im2col_fwd",
@@ -163,7 +164,9 @@ def load() -> C.CDLL:
     lib.ag_rmsnorm_fwd.argtypes = [P] * 4 + [I64, I32, C.c_int, P]
     lib.ag_add_embed_norm_fwd.argtypes = [P] * 6 + [I32] * 3 + [C.c_int, P]
     lib.ag_pair_out_embed_fwd.argtypes = [P] * 6 + [I32] * 4 + [C.c_int, P]
-    for name in EXPORTED[5:]:
+    lib.ag_gemm_set_cta_group.argtypes = [C.c_int]
+    lib.ag_gemm_set_cta_group.restype = C.c_int
+    for name in EXPORTED[6:]:
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

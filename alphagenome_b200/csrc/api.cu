@@ -11,6 +11,7 @@ namespace agb {
 
 static thread_local char tl_error[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_gemm_cta_group{0};   // see ag_gemm_set_cta_group
 static std::mutex g_mu;
 static unsigned int* g_err_host[64] = {nullptr};
 static unsigned int* g_err_dev[64] = {nullptr};
@@ -127,6 +128,11 @@ int ag_watchdog_status(int device, uint32_t out[4]) {
   }
   for (int i = 0; i < 4; ++i) out[i] = g_err_host[device][i];
   return out[0] != 0;
+}
+
+int ag_gemm_set_cta_group(int cta_group) {
+  if (cta_group < 0 || cta_group > 2) return -1;
+  return agb::g_gemm_cta_group.exchange(cta_group);
 }
 
 int ag_gemm_fwd(const AgGemmArgs* args, int device, void* stream) {

@@ -16,6 +16,8 @@
 //                      fused affine / ReLU / residual / scale / activation / maxpool2 -> 128-bit global accesses.
 //                      The kernel is instantiated per set of enabled outputs (template FLAGS) so disabled paths
 //                      cost no instructions; all pointer arithmetic is hoisted to one 64-bit base per tile.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,7 +25,7 @@ namespace agb {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kStages = 4;
+
 constexpr int kMaxNTile = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kBBytesMax = kMaxNTile * kBlockK * 2; // 32 KB
@@ -32,7 +34,15 @@ constexpr int kEpiCols = 16;                          // columns per TMEM load /
 constexpr int kEpiBytesPerWarp = 32 * kEpiCols * 4;   // 2 KB, XOR-swizzled (no padding)
 constexpr int kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
-constexpr int kGemmSmem = 1024 /*align slack*/ + kStages * (kABytes + kBBytesMax) + kEpiBytes + 256;
+// CG = CTAs per MMA (tcgen05 cta_group).  CG = 2: a cluster of two CTAs computes a 256 x n_tile tile; each CTA stages
+// its own 128 rows of A and half of the W tile (<= 16 KB), which leaves room for a 6-deep ring.
+template <int CG> struct GemmCfg;
+template <> struct GemmCfg<1> { static constexpr int kStg = 4, kBBytes = kBBytesMax; };
+template <> struct GemmCfg<2> { static constexpr int kStg = 6, kBBytes = kBBytesMax / 2; };
+template <int CG>
+constexpr int gemm_smem_bytes() {
+  return 1024 /*align slack*/ + GemmCfg<CG>::kStg * (kABytes + GemmCfg<CG>::kBBytes) + kEpiBytes + 256;
+}
 
 enum : int { F_RES = 1, F_OUT = 2, F_ACTA = 4, F_ACTB = 8, F_POOL = 16, F_COUNT = 32 };
 
@@ -40,7 +50,7 @@ struct GemmKParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
   AgGemmArgs g;
-  int n_tile, m_tiles, n_tiles, total_tiles, kblocks;
+  int n_tile, m_tiles, n_tiles, total_tiles, kblocks;   // m_tiles counts (128 * CG)-row tiles
   unsigned int* err;
 };
 
@@ -88,25 +98,30 @@ __device__ __forceinline__ float4 ldg4_or(const float* p, float dflt) {
   return make_float4(dflt, dflt, dflt, dflt);
 }
 
-template <int FLAGS>
+template <int FLAGS, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid_constant__ GemmKParams p) {
+  constexpr int kStages = GemmCfg<CG>::kStg;
+  constexpr int kBStage = GemmCfg<CG>::kBBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);   // same offset in both CTAs of a pair
 
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kABytes;
-  uint8_t* sEpi = smem + kStages * (kABytes + kBBytesMax);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytesMax) + kEpiBytes);
-  uint64_t* full_bar = bars;                 // [kStages]
+  uint8_t* sEpi = smem + kStages * (kABytes + kBStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBStage) + kEpiBytes);
+  uint64_t* full_bar = bars;                 // [kStages]   (CG = 2: only the leader CTA's are used)
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]   (CG = 2: the leader's, arrived on by both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const AgGemmArgs& g = p.g;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -117,40 +132,53 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
+      mbar_init(&tempty_bar[i], kEpiWarps * CG);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, 512);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int iters = g.taps * p.kblocks;
-  const uint32_t b_bytes = (uint32_t)p.n_tile * kBlockK * 2;
+  const uint32_t b_bytes = (uint32_t)(p.n_tile / CG) * kBlockK * 2;   // this CTA's share of the W tile
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
         const int mt = rest % p.m_tiles;
         const int b = rest / p.m_tiles;
-        const int row0 = g.a_row0 + mt * kBlockM - g.taps / 2;
+        const int row0 = g.a_row0 + (mt * CG + (int)crank) * kBlockM - g.taps / 2;
+        const int wrow0 = nt * p.n_tile + (int)crank * (p.n_tile / CG);
         for (int tap = 0; tap < g.taps; ++tap) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u, 0x10u + stage, p.err);
-            mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
-            tma_load_3d(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b);
-            tma_load_3d(sB + stage * kBBytesMax, &p.tmB, &full_bar[stage], kb * kBlockK, nt * p.n_tile,
-                        g.w_batched ? b : tap);
+            if constexpr (CG == 2) {
+              // both CTAs' boxes complete on the leader's barrier, which expects the pair's bytes
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (kABytes + b_bytes));
+              tma_load_3d_cg2(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b);
+              tma_load_3d_cg2(sB + stage * kBStage, &p.tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
+              tma_load_3d(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b);
+              tma_load_3d(sB + stage * kBStage, &p.tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -159,13 +187,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.n_tile);
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM * CG, (uint32_t)p.n_tile);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[as], aphase ^ 1u, 0x30u + as, p.err);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * kMaxNTile;
@@ -173,16 +201,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           mbar_wait(&full_bar[stage], phase, 0x20u + stage, p.err);
           tc_fence_after();
           const uint64_t da = make_sw128_kmajor_desc(smem_u32(sA + stage * kABytes));
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(sB + stage * kBBytesMax));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(sB + stage * kBStage));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128B swizzle atom (encoded >>4 -> +2)
-            tc_mma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2)
+              tc_mma_bf16_ss_cg2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else
+              tc_mma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);
+          if constexpr (CG == 2) tc_commit_cg2(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(&tfull_bar[as]);
+        if constexpr (CG == 2) tc_commit_cg2(&tfull_bar[as]); else tc_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -212,13 +243,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     const bool p16 = g.actP.dtype == 0, pG = g.actP.act != ACT_NONE;
     const bool has_poolf = kPool && g.pool != nullptr, has_actP = kPool && g.actP.ptr != nullptr;
     const int nchunks = p.n_tile / kEpiCols;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
       const int n0 = nt * p.n_tile;
-      const int row_t = mt * kBlockM;              // first row of the tile
+      const int row_t = (mt * CG + (int)crank) * kBlockM;   // first row of this CTA's 128-row tile
       const int lr_base = q * 32;                  // this warp's rows inside the tile
       // one 64-bit base per tensor per tile; everything below is 32-bit in-tile offsets
       const float* res_t = kRes ? g.res + (long)b * g.res_bstride + (long)(row_t >> g.res_shift) * g.res_ld + n0 : nullptr;
@@ -317,16 +348,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0u);   // the leader's MMA thread owns the accumulators
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // neither CTA leaves while the pair's MMAs / arrives may still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -335,10 +371,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
 // ----------------------------------------------------------------------------------------------------
 typedef void (*GemmKernelFn)(const GemmKParams);
 
-// one instantiation per set of enabled outputs (res / out / actA / actB / pool)
+// one instantiation per set of enabled outputs (res / out / actA / actB / pool) and per CTA-group size
 template <int... I>
 struct GemmTable {
-  GemmKernelFn fn[sizeof...(I)] = {gemm_conv_kernel<I>...};
+  GemmKernelFn fn1[sizeof...(I)] = {gemm_conv_kernel<I, 1>...};
+  GemmKernelFn fn2[sizeof...(I)] = {gemm_conv_kernel<I, 2>...};
 };
 template <int N, int... I>
 struct MakeGemmTable : MakeGemmTable<N - 1, N - 1, I...> {};
@@ -347,6 +384,18 @@ struct MakeGemmTable<0, I...> {
   typedef GemmTable<I...> type;
 };
 static const MakeGemmTable<F_COUNT>::type kGemmTable;
+
+// env AGB_GEMM_CG=1|2 seeds ag_gemm_set_cta_group() (A/B timing, bring-up); default 0 = pairs whenever there are
+// at least two 128-row tiles
+static int forced_cg() {
+  static bool seeded = false;
+  if (!seeded) {
+    seeded = true;
+    const char* e = getenv("AGB_GEMM_CG");
+    if (e && (e[0] == '1' || e[0] == '2') && g_gemm_cta_group.load() == 0) g_gemm_cta_group.store(e[0] - '0');
+  }
+  return g_gemm_cta_group.load();
+}
 
 static int pick_n_tile(int N) {
   for (int t = 256; t >= 16; t -= 16)
@@ -389,7 +438,9 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   p.g = a;
   p.n_tile = pick_n_tile(a.N);
   if (!p.n_tile) return set_error("ag_gemm_fwd: no N tile for N=%d", a.N);
-  p.m_tiles = (a.M + kBlockM - 1) / kBlockM;
+  int cg = forced_cg();
+  if (cg == 0) cg = a.M > kBlockM ? 2 : 1;
+  p.m_tiles = (a.M + kBlockM * cg - 1) / (kBlockM * cg);
   p.n_tiles = a.N / p.n_tile;
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
   p.kblocks = (a.K + kBlockK - 1) / kBlockK;
@@ -405,22 +456,38 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
     const int nz = a.w_batched ? a.batch : a.taps;
     uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)(a.w_rows > 0 ? a.w_rows : a.N), (uint64_t)nz};
     uint64_t strides[2] = {(uint64_t)a.w_ld * 2, (uint64_t)(nz > 1 ? a.w_zstride : (int64_t)a.w_ld * (a.w_rows > 0 ? a.w_rows : a.N)) * 2};
-    uint32_t box[3] = {kBlockK, (uint32_t)p.n_tile, 1};
+    uint32_t box[3] = {kBlockK, (uint32_t)(p.n_tile / cg), 1};   // a CTA of a pair stages half of the W tile
     if (int rc = make_tensor_map_bf16(&p.tmB, a.W, 3, dims, strides, box)) return rc;
   }
 
   const int flags = (a.res ? F_RES : 0) | (a.out ? F_OUT : 0) | (a.actA.ptr ? F_ACTA : 0) | (a.actB.ptr ? F_ACTB : 0) |
                     ((a.pool || a.actP.ptr) ? F_POOL : 0);
   if (flags == 0) return set_error("ag_gemm_fwd: no output requested");
-  GemmKernelFn fn = kGemmTable.fn[flags];
-  static thread_local unsigned char attr_done[64][F_COUNT];
-  if (!attr_done[device][flags]) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+  GemmKernelFn fn = cg == 2 ? kGemmTable.fn2[flags] : kGemmTable.fn1[flags];
+  const int smem = cg == 2 ? gemm_smem_bytes<2>() : gemm_smem_bytes<1>();
+  static thread_local unsigned char attr_done[64][2][F_COUNT];
+  if (!attr_done[device][cg - 1][flags]) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error("ag_gemm_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_done[device][flags] = 1;
+    attr_done[device][cg - 1][flags] = 1;
   }
-  int grid = p.total_tiles < sm_count(device) ? p.total_tiles : sm_count(device);
-  fn<<<grid, kGemmThreads, kGemmSmem, stream>>>(p);
+  const int units = sm_count(device) / cg;   // persistent: one CTA (or CTA pair) per SM (or TPC)
+  const int grid = (p.total_tiles < units ? p.total_tiles : units) * cg;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
+  if (le != cudaSuccess) return set_error("ag_gemm_fwd: launch failed: %s", cudaGetErrorString(le));
   return check_launch("ag_gemm_fwd");
 }
 

@@ -1,5 +1,7 @@
 // Internal host-side declarations shared by the .cu files of libagb200.so (not part of the C ABI).
 #pragma once
+#include <atomic>
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,6 +22,7 @@ int sm_count(int device);
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box);
 
+extern std::atomic<int> g_gemm_cta_group;   // 0 auto, 1, 2 (ag_gemm_set_cta_group)
 int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream);
 int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream);
 int launch_onehot_im2col(const int64_t* tokens, void* out, int B, int L, int width, int n_base, int ld, int device,

@@ -179,6 +179,13 @@ def gemm(
     _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
 
 
+def set_gemm_cta_group(cta_group: int) -> int:
+    """ag_gemm_set_cta_group: 0 = automatic, 1 = single-CTA MMAs, 2 = CTA pairs.  Returns the previous setting."""
+    prev = _lib.load().ag_gemm_set_cta_group(int(cta_group))
+    _require(prev >= 0, f"bad cta_group {cta_group}")
+    return prev
+
+
 def _dev(t: torch.Tensor) -> int:
     return t.device.index or 0
 

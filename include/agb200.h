@@ -206,6 +206,10 @@ int ag_check_device(int device);
 /* device watchdog: a kernel whose mbarrier wait exceeds ~4 s records {0xDEAD0000|tag, blockIdx, threadIdx, parity}
  * in host-mapped memory and traps (never hangs the GPU); returns non-zero if such a record exists. */
 int ag_watchdog_status(int device, uint32_t out[4]);
+/* tuning / bring-up hook with no reference counterpart: CTAs per tcgen05.mma in ag_gemm_fwd.  0 = automatic (CTA pairs,
+ * cta_group::2, whenever the problem has at least two 128-row tiles), 1 = single-CTA MMAs, 2 = pairs.  Results are
+ * bit-identical either way (same products, same fp32 accumulation order); returns the previous setting. */
+int ag_gemm_set_cta_group(int cta_group);
 
 #ifdef __cplusplus
 }

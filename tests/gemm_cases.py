@@ -39,7 +39,7 @@ def ref_acc(A, W, M, a_row0, w_batched):
     return acc
 
 
-def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogue="plain", seed=0, strided=False):
+def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogue="plain", seed=0, strided=False, cta_group=0):
     """Returns dict(name, ok, max_err, details...). Tolerance: fp32-accumulate of bf16 products, so the only
     error is summation order -> 2e-3 relative to the output scale is generous and still catches any
     descriptor/layout bug (those give O(1) errors)."""
@@ -104,8 +104,12 @@ def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogu
     else:
         raise ValueError(epilogue)
 
-    ops.gemm(A, W, M=M, a_row0=a_row0, w_batched=w_batched, **kw)
-    torch.cuda.synchronize()
+    prev = ops.set_gemm_cta_group(cta_group)   # 0 auto, 1 single-CTA MMAs, 2 CTA pairs (cta_group::2)
+    try:
+        ops.gemm(A, W, M=M, a_row0=a_row0, w_batched=w_batched, **kw)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_cta_group(prev)
 
     ok = True
     worst = 0.0
@@ -135,4 +139,11 @@ CASES = [
     dict(name="batched_heads_strided", batch=8, M=96, K=128, N=96, w_batched=True, strided=True),
     dict(name="persistent_many_tiles", batch=1, M=128 * 700, K=128, N=256),
     dict(name="conv5_big", batch=1, M=16384, K=768, N=768, taps=5, epilogue="full"),
+    # CTA-pair specifics: second CTA of the last pair entirely / partly outside M, N tiles 224 and 176 split in halves,
+    # a deep K loop that wraps the 6-stage ring many times, N = 16 (8-row W halves)
+    dict(name="pair_m_tail_empty_peer", batch=1, M=128 * 5 + 7, K=256, N=256, epilogue="relu_bf16"),
+    dict(name="pair_n224_conv5", batch=1, M=1024, K=768, N=896, taps=5),
+    dict(name="pair_n176_full_epi", batch=2, M=768, K=320, N=1408, epilogue="full"),
+    dict(name="pair_deep_k", batch=1, M=512, K=3072, N=1536),
+    dict(name="pair_n16", batch=1, M=4096, K=128, N=16),
 ]
