@@ -274,10 +274,7 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_eager = tms.tolist()
     if rank != 0:
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.barrier()
+        finish(world)
         return
     pk = peaks()
     value = B * L / (ms * 1e-3)            # whole job: one context over all `world` GPUs
@@ -302,11 +299,23 @@ def main():
         line["cpu_baseline"] = dict(value=bps, unit=UNIT, cores=cores, kind="port", seconds=secs,
                                     sample=f"one forward of B=1 x {CPU_SAMPLE_L} bp (1/8 of the workload) through the pinned CPU oracle, fp32")
     print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
+    finish(world)
 
-        dist.barrier()
-        dist.destroy_process_group()
+
+def finish(world):
+    """Leave a multi-rank run without a collective teardown.  Every rank synchronises its device, meets the others at a
+    last barrier and exits the process directly: destroy_process_group() / interpreter finalisation with captured NCCL
+    kernels still referenced by CUDA graphs hung the 8-GPU run after the result line had been printed."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
