@@ -12,8 +12,9 @@ bin is rank-local):
                            everything inside the owned range is exact; at the two true sequence ends there is no
                            halo and the window edge IS the reference's zero padding.  Costs 2*2048/(L/G) extra
                            conv work (3 % at 1 Mbp / 8 GPUs) and only ONE exchange (16 tower-output tokens per
-                           side) instead of 27 per-layer halo exchanges.
-  tower attention          Q local; K [n,128] and V [n,192] all-gathered per layer (bf16).  Bias rows are local.
+                           side, fp32 residual + bf16 operand packed into one collective) instead of 27
+                           per-layer halo exchanges.
+  tower attention          Q local; [K | V] = [n,128+192] bf16 all-gathered per layer in ONE collective.  Bias rows local.
   pair blocks              pooled/normalised single rows all-gathered (bf16 [P,1536] x2); q.k and rel-pos GEMMs,
                            row attention, FF and the bias projection run on local rows only.
   pair output embedding    symmetrize needs pair[j, i]: one all_to_all of [P/G x P/G] blocks.
@@ -140,13 +141,33 @@ class SeqParallel:
     def exchange_halo(self, x: torch.Tensor, h: int):
         """x: [B, rows, C]; returns (left, right): the last h rows of rank-1 and the first h rows of rank+1
         (None at the two sequence ends)."""
-        B, r, C = x.shape
-        edges = torch.stack((x[:, :h], x[:, r - h:]), dim=0).contiguous()  # [2, B, h, C]
-        out = torch.empty(self.world, 2, B, h, C, dtype=x.dtype, device=x.device)
-        self._all_gather(out, edges)
-        left = out[self.rank - 1, 1] if self.rank > 0 else None
-        right = out[self.rank + 1, 0] if self.rank < self.world - 1 else None
+        (left, right), = self.exchange_halos([x], h)
         return left, right
+
+    def exchange_halos(self, xs, h: int):
+        """Several [B, rows, C_i] tensors (any dtypes, same B and rows) in ONE collective: their edge rows are packed
+        as bytes.  Returns [(left_i, right_i), ...] like exchange_halo."""
+        B, r = xs[0].shape[0], xs[0].shape[1]
+        parts = []
+        for x in xs:
+            edges = torch.stack((x[:, :h], x[:, r - h:]), dim=0).contiguous()          # [2, B, h, C]
+            parts.append(edges.view(torch.uint8).view(2, B, h, -1))                     # bytes of each row
+        packed = torch.cat(parts, dim=-1).contiguous() if len(parts) > 1 else parts[0]
+        nb = packed.shape[-1]
+        out = torch.empty(self.world, 2, B, h, nb, dtype=torch.uint8, device=packed.device)
+        self._all_gather(out, packed)
+        res, off = [], 0
+        for x in xs:
+            w = x.shape[2] * x.element_size()
+
+            def take(side_rank, side):
+                return out[side_rank, side, :, :, off:off + w].contiguous().view(x.dtype).view(B, h, x.shape[2])
+
+            left = take(self.rank - 1, 1) if self.rank > 0 else None
+            right = take(self.rank + 1, 0) if self.rank < self.world - 1 else None
+            res.append((left, right))
+            off += w
+        return res
 
     def transpose_blocks(self, pair: torch.Tensor) -> torch.Tensor:
         """pair: this rank's rows [B, P_loc, P, C] -> pairT [world, B, P_loc, P_loc, C] with

@@ -327,15 +327,15 @@ class TrunkEngine:
             V = torch.empty(B, n, dv, **bf)
             ops.qkv_post(qkv, Q, K, V, cos_t, sin_t, at["qw"], at["qb"], at["kw"], at["kb"], at["vw"], at["vb"], Hh, d, dv)
             if sharded:  # K/V of every rank (AG:748 attends over the whole context); Q and the bias rows stay local
-                K = self.sp.gather_rows(K)
-                V = self.sp.gather_rows(V)
+                KV = self.sp.gather_rows(torch.cat((K, V), dim=-1))   # ONE all-gather per layer: [B, n_all, d + dv]
+                K, V = KV[..., :d], KV[..., d:]                         # strided views (TMA / transpose take a row stride)
             nk = _round_up(n_all, 8)
             Vt = torch.empty(B, dv, nk, **bf)
             ops.transpose_bf16(V, Vt)
             bias = torch.empty(B, Hh, pair.shape[1], pair.shape[2], **f32)
             ops.pair_bias(pair, at["ab_s"], at["ab_t"], at["ab_W"], bias)
             O = torch.empty(B, n, Hh * dv, **bf)
-            ops.attention(Q.view(B, n, Hh, d).permute(0, 2, 1, 3), K.view(B, 1, n_all, d), Vt.view(B, 1, dv, nk),
+            ops.attention(Q.view(B, n, Hh, d).permute(0, 2, 1, 3), K.unsqueeze(1), Vt.view(B, 1, dv, nk),
                           O.view(B, n, Hh, dv).permute(0, 2, 1, 3), mode=0, scale=at["scale"], bias=bias, softcap=at["softcap"])
             ff = L["ff"]
             ops.gemm(O, at["Wout"], pre_scale=at["out_scale"], pre_shift=at["out_shift"], res=single, out=single,
@@ -414,8 +414,7 @@ class TrunkEngine:
             # the decoder's receptive field reaches 6 tokens into the neighbours: fetch halo tokens of the tower
             # output (fp32 residual + the pre-activated bf16 operand) and run the decoder on the extended window
             ht = self.sp.halo_bp // 128
-            l32, r32 = self.sp.exchange_halo(single, ht)
-            l16, r16 = self.sp.exchange_halo(a_dec, ht)
+            (l32, r32), (l16, r16) = self.sp.exchange_halos([single, a_dec], ht)   # one collective for both
             x_dec = torch.cat([t for t in (l32, single, r32) if t is not None], dim=1)
             a_dec = torch.cat([t for t in (l16, a_dec, r16) if t is not None], dim=1)
         unet_out, unet_b16 = self._decoder(P, x_dec, a_dec, skips, want_plain=with_embeds)

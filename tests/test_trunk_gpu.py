@@ -121,3 +121,31 @@ def test_sequence_parallel_matches_single_rank():
     assert lines, (p.returncode, p.stdout[-2000:], p.stderr[-3000:])
     rec = json.loads(lines[-1][9:])
     assert rec["ok"], rec
+
+
+def test_host_pipeline_matches_direct_calls():
+    """HostPipeline (double-buffered H2D / forward / D2H) returns, per step, exactly what model(dna, org) returns."""
+    import numpy as np
+
+    from alphagenome_b200.init_weights import apply_synth_weights
+    from alphagenome_b200.model import AlphaGenome
+    from alphagenome_b200.pipeline import HostPipeline
+
+    model = AlphaGenome().cuda().eval()
+    apply_synth_weights(model, seed=3)
+    model.enable_cuda_graphs(True)
+    rng = np.random.default_rng(5)
+    batches = [(torch.from_numpy(rng.integers(0, 4, size=(1, 4096)).astype(np.int64)).pin_memory(),
+                torch.tensor([i % 2], dtype=torch.long).pin_memory()) for i in range(5)]
+    want = []
+    for tok, org in batches:
+        emb = model(tok.cuda(), org.cuda())
+        want.append((emb.embeds_128bp.cpu().clone(), emb.embeds_pair.cpu().clone()))
+    got = {}
+    pipe = HostPipeline(model)
+    n = pipe.run(iter(batches), consume=lambda i, outs: got.__setitem__(i, [o.clone() for o in outs]))
+    torch.cuda.synchronize()
+    assert n == 5 and sorted(got) == list(range(5))
+    for i in range(5):
+        assert torch.equal(got[i][0], want[i][0]) and torch.equal(got[i][1], want[i][1])
+    assert pipe.d2h_bytes == 5 * sum(t.numel() * 4 for t in want[0])
