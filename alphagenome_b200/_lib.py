@@ -100,6 +100,9 @@ class AgAttnArgs(C.Structure):
         ("res", C.c_void_p),
         ("bias_rows", C.c_int32),
         ("reserved1", C.c_int32),
+        ("norm_w", C.c_void_p),
+        ("norm_b", C.c_void_p),
+        ("norm_out", C.c_void_p),
     ]
 
 
@@ -158,9 +161,9 @@ def load() -> C.CDLL:
     lib.ag_onehot_im2col_fwd.argtypes = [P, P, I32, I32, I32, I32, I32, C.c_int, P]
     lib.ag_qkv_post_fwd.argtypes = [P] * 12 + [I32] * 5 + [C.c_int, P]
     lib.ag_transpose_bf16.argtypes = [P, P, I32, I32, I32, I64, I32, I64, I32, C.c_int, P]
-    lib.ag_pair_bias_fwd.argtypes = [P] * 5 + [I32] * 5 + [C.c_int, P]
+    lib.ag_pair_bias_fwd.argtypes = [P] * 5 + [I32] * 6 + [I64, C.c_int, P]
     lib.ag_pool_rmsnorm_fwd.argtypes = [P] * 5 + [I32] * 4 + [C.c_int, P]
-    lib.ag_pair_combine_fwd.argtypes = [P] * 8 + [I32] * 8 + [C.c_int, P]
+    lib.ag_pair_combine_fwd.argtypes = [P] * 11 + [I32] * 8 + [C.c_int, P]
     lib.ag_rmsnorm_fwd.argtypes = [P] * 4 + [I64, I32, C.c_int, P]
     lib.ag_add_embed_norm_fwd.argtypes = [P] * 6 + [I32] * 3 + [C.c_int, P]
     lib.ag_pair_out_embed_fwd.argtypes = [P] * 6 + [I32] * 4 + [C.c_int, P]

@@ -170,9 +170,11 @@ int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t 
 }
 
 int ag_pair_bias_fwd(const float* pair, const float* scale, const float* shift, const float* W, float* bias, int32_t B,
-                     int32_t rows, int32_t cols, int32_t C, int32_t heads, int device, void* stream) {
+                     int32_t rows, int32_t cols, int32_t C, int32_t heads, int32_t sets, int64_t set_stride, int device,
+                     void* stream) {
   if (int rc = ensure_device(device)) return rc;
-  return launch_pair_bias(pair, scale, shift, W, bias, B, rows, cols, C, heads, device, static_cast<cudaStream_t>(stream));
+  return launch_pair_bias(pair, scale, shift, W, bias, B, rows, cols, C, heads, sets, set_stride, device,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int ag_pool_rmsnorm_fwd(const float* single, const float* w, const float* b, void* x_bf16, void* xg_bf16, int32_t B,
@@ -182,11 +184,12 @@ int ag_pool_rmsnorm_fwd(const float* single, const float* w, const float* b, voi
 }
 
 int ag_pair_combine_fwd(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
-                        const float* outer, const float* prev, float* pair, int32_t B, int32_t P, int32_t H, int32_t D,
-                        int32_t qk_ld, int32_t rel_ld, int32_t rows, int32_t i_off, int device, void* stream) {
+                        const float* outer, const float* prev, float* pair, const float* norm_w, const float* norm_b,
+                        void* pair_norm_bf16, int32_t B, int32_t P, int32_t H, int32_t D, int32_t qk_ld, int32_t rel_ld,
+                        int32_t rows, int32_t i_off, int device, void* stream) {
   if (int rc = ensure_device(device)) return rc;
-  return launch_pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair, B, P, H, D, qk_ld, rel_ld, rows, i_off, device,
-                             static_cast<cudaStream_t>(stream));
+  return launch_pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair, norm_w, norm_b, pair_norm_bf16, B, P, H, D, qk_ld,
+                             rel_ld, rows, i_off, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_rmsnorm_fwd(const float* x, const float* w, const float* b, void* out_bf16, int64_t rows, int32_t C, int device,

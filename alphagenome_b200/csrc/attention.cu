@@ -337,6 +337,57 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     tc_fence_after();
     const long obase = (long)b * a.out_bstride + (long)h * a.out_hstride + (long)row * a.out_ld;
     const int cbeg = cq * (dv / 4), cend = cbeg + dv / 4;
+    if (a.norm_out != nullptr) {
+      // fp32 out + bias + residual, and RMSNormWithBias of the finished row in bf16 (dv == 128: this thread holds
+      // 32 of the row's 128 channels; the sum of squares is exchanged between the four column quarters)
+      float y[32];
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_O + lane_off + (uint32_t)(cbeg + 16 * hc), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[16 * hc + j] = __uint_as_float(r[j]) * inv;
+      }
+      float ss = 0.f;
+      if (row < a.n_q) {
+        float* o = reinterpret_cast<float*>(a.out) + obase + cbeg;
+        const float* rs = a.res ? a.res + obase + cbeg : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (a.out_bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.out_bias + cbeg + j));
+            y[j] += bb.x; y[j + 1] += bb.y; y[j + 2] += bb.z; y[j + 3] += bb.w;
+          }
+          if (rs) {
+            const float4 rr = *reinterpret_cast<const float4*>(rs + j);
+            y[j] += rr.x; y[j + 1] += rr.y; y[j + 2] += rr.z; y[j + 3] += rr.w;
+          }
+          *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          ss += y[j] * y[j] + y[j + 1] * y[j + 1] + y[j + 2] * y[j + 2] + y[j + 3] * y[j + 3];
+        }
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // every thread has read the row sums from xch
+      xch[cq * 128 + lrow] = ss;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (row < a.n_q) {
+        const float rinv = rsqrtf(((xch[lrow] + xch[128 + lrow]) + (xch[256 + lrow] + xch[384 + lrow])) * (1.0f / 128.0f) + 1e-5f);
+        __nv_bfloat16* no = reinterpret_cast<__nv_bfloat16*>(a.norm_out) + obase + cbeg;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.norm_w + cbeg + j));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.norm_w + cbeg + j + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.norm_b + cbeg + j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.norm_b + cbeg + j + 4));
+          uint4 pk;
+          pk.x = pack_bf16x2(fmaf(y[j] * rinv, w0.x, b0.x), fmaf(y[j + 1] * rinv, w0.y, b0.y));
+          pk.y = pack_bf16x2(fmaf(y[j + 2] * rinv, w0.z, b0.z), fmaf(y[j + 3] * rinv, w0.w, b0.w));
+          pk.z = pack_bf16x2(fmaf(y[j + 4] * rinv, w1.x, b1.x), fmaf(y[j + 5] * rinv, w1.y, b1.y));
+          pk.w = pack_bf16x2(fmaf(y[j + 6] * rinv, w1.z, b1.z), fmaf(y[j + 7] * rinv, w1.w, b1.w));
+          *reinterpret_cast<uint4*>(no + j) = pk;
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cend; c0 += 16) {
       uint32_t r[16];
@@ -376,6 +427,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
           }
         }
       }
+    }
     }
     tc_fence_before();
   }
@@ -417,6 +469,8 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
   if ((a.out_ld | a.out_hstride | a.out_bstride) % 8) return set_error("ag_attention_fwd: out strides must be multiples of 8 elements");
 
   if (reinterpret_cast<uintptr_t>(a.Q) & 15) return set_error("ag_attention_fwd: Q must be 16-byte aligned");
+  if (a.norm_out && (a.out_dtype != 1 || a.dv != 128 || !a.norm_w || !a.norm_b))
+    return set_error("ag_attention_fwd: the normalised output needs fp32 out, dv == 128 and norm_w/norm_b");
   AttnKParams p;
   memset(&p, 0, sizeof(p));
   p.a = a;

@@ -141,30 +141,110 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv
 }
 
 // ---------------------------------------------------------------------------------------------------
-// to_attn_bias (AG:688-693).  One warp per pair cell: float4 per lane (C = 128), 8 dot products, butterfly.
+// to_attn_bias (AG:688-693) for up to two attention layers that read the same pair tensor (the pair only changes
+// on every second tower layer), in ONE pass over it.  A warp takes 8 consecutive cells: float4 per lane (C = 128),
+// per cell sets*8 partial dot products, reduced over the 32 lanes with a transposing butterfly (16 + 8 + 4 + 2 + 2
+// values exchanged instead of 5 shuffles per value); lane l ends up owning output plane l >> 1 and writes its 8
+// cells as two float4 (full 32-byte sectors).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, two MUFU ops).
 // ---------------------------------------------------------------------------------------------------
-__global__ void pair_bias_kernel(const float* __restrict__ pair, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, const float* __restrict__ W, float* __restrict__ bias,
-                                 int B, int rows, int cols, int heads) {
+__device__ __forceinline__ float gelu_erf_as(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);     // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+template <int SETS>
+__global__ void __launch_bounds__(256) pair_bias_kernel(const float* __restrict__ pair, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, const float* __restrict__ W,
+                                                        float* __restrict__ bias, long groups, long per_b, int heads,
+                                                        long set_stride) {
+  constexpr int NV = SETS * 8;   // values per cell (heads == 8)
   const int lane = threadIdx.x & 31;
-  const long per_b = (long)rows * cols;
-  const long cells = (long)B * per_b;
-  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + lane);
-  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + lane);
-  for (long cell = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; cell < cells;
+  float4 sc[SETS], sh[SETS];
+#pragma unroll
+  for (int s = 0; s < SETS; ++s) {
+    sc[s] = __ldg(reinterpret_cast<const float4*>(scale + s * 128) + lane);
+    sh[s] = __ldg(reinterpret_cast<const float4*>(shift + s * 128) + lane);
+  }
+  const int plane = lane >> (SETS == 2 ? 1 : 2);   // output plane (set * 8 + head) this lane ends up owning
+  for (long grp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; grp < groups; grp += ((long)gridDim.x * blockDim.x) >> 5) {
+    const long cell0 = grp * 8;
+    float4 x[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = __ldg(reinterpret_cast<const float4*>(pair + (cell0 + c) * 128) + lane);
+    float res[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v[NV];
+#pragma unroll
+      for (int s = 0; s < SETS; ++s) {
+        float4 y;
+        y.x = gelu_erf_as(fmaf(x[c].x, sc[s].x, sh[s].x));
+        y.y = gelu_erf_as(fmaf(x[c].y, sc[s].y, sh[s].y));
+        y.z = gelu_erf_as(fmaf(x[c].z, sc[s].z, sh[s].z));
+        y.w = gelu_erf_as(fmaf(x[c].w, sc[s].w, sh[s].w));
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(W + (s * 8 + g) * 128) + lane);
+          v[s * 8 + g] = y.x * w.x + y.y * w.y + y.z * w.z + y.w * w.w;
+        }
+      }
+      // transposing butterfly: after the step with offset o, a lane keeps the half of its values selected by (lane & o)
+#pragma unroll
+      for (int n = NV, o = 16; n > 1; n >>= 1, o >>= 1) {
+        const bool hi = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+          const float send = hi ? v[i] : v[i + n / 2];
+          const float keep = hi ? v[i + n / 2] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      // SETS == 2: 16 values used offsets 16..2, one more plain step; SETS == 1: 8 values used 16..4, two more
+      float r = v[0];
+#pragma unroll
+      for (int o = (SETS == 2 ? 1 : 2); o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+      res[c] = r;
+    }
+    if ((lane & (SETS == 2 ? 1 : 3)) == 0) {
+      const long b = cell0 / per_b;
+      const long ij = cell0 - b * per_b;
+      const int set = plane >> 3, g = plane & 7;
+      float* dst = bias + set * set_stride + (b * heads + g) * per_b + ij;
+      reinterpret_cast<float4*>(dst)[0] = make_float4(res[0], res[1], res[2], res[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(res[4], res[5], res[6], res[7]);
+    }
+  }
+}
+
+// cells that do not fill a group of 8 (or unaligned shapes): one warp per cell, plain reduction
+__global__ void pair_bias_tail_kernel(const float* __restrict__ pair, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, const float* __restrict__ W, float* __restrict__ bias,
+                                      long cell_begin, long cells, long per_b, int heads, int sets, long set_stride) {
+  const int lane = threadIdx.x & 31;
+  for (long cell = cell_begin + ((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5); cell < cells;
        cell += ((long)gridDim.x * blockDim.x) >> 5) {
-    float4 x = __ldg(reinterpret_cast<const float4*>(pair + cell * 128) + lane);
-    x.x = act_apply(fmaf(x.x, sc.x, sh.x), ACT_GELU_ERF);
-    x.y = act_apply(fmaf(x.y, sc.y, sh.y), ACT_GELU_ERF);
-    x.z = act_apply(fmaf(x.z, sc.z, sh.z), ACT_GELU_ERF);
-    x.w = act_apply(fmaf(x.w, sc.w, sh.w), ACT_GELU_ERF);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(pair + cell * 128) + lane);
     const long b = cell / per_b;
     const long ij = cell - b * per_b;
-    for (int g = 0; g < heads; ++g) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(W + g * 128) + lane);
-      float d = x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w;
-      d = warp_sum(d);
-      if (lane == 0) bias[(b * heads + g) * per_b + ij] = d;
+    for (int s = 0; s < sets; ++s) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + s * 128) + lane);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + s * 128) + lane);
+      float4 y;
+      y.x = gelu_erf_as(fmaf(x.x, sc.x, sh.x));
+      y.y = gelu_erf_as(fmaf(x.y, sc.y, sh.y));
+      y.z = gelu_erf_as(fmaf(x.z, sc.z, sh.z));
+      y.w = gelu_erf_as(fmaf(x.w, sc.w, sh.w));
+      for (int g = 0; g < heads; ++g) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + (s * heads + g) * 128) + lane);
+        const float d = warp_sum(y.x * w.x + y.y * w.y + y.z * w.z + y.w * w.w);
+        if (lane == 0) bias[s * set_stride + (b * heads + g) * per_b + ij] = d;
+      }
     }
   }
 }
@@ -204,46 +284,136 @@ __global__ void pool_rmsnorm_kernel(const float* __restrict__ single, const floa
 }
 
 // ---------------------------------------------------------------------------------------------------
-// SingleToPairwise combine (AG:835-856, relative_shift AG:523-530).  Block = (b, i, 32 consecutive j).
-// Phase 1: 256 threads compute sim[j][h] (32 x 32) into smem; phase 2: thread = output channel.
+// SingleToPairwise combine (AG:835-856, relative_shift AG:523-530) + the pre-norm of the row attention that
+// consumes the result (RMSNormWithBias, AG:400-405, via NormWrapper AG:974).
+// Block = (b, 8 rows i, 32 columns j), 256 threads.
+//   phase 1: sim[i][h][j] = qk[h][i][j] + 0.5 (relq[h][i][P+j-i] + relk[h][j][P+i-j]) into smem.  qk / relq are read
+//            with j fastest (coalesced); relk with i fastest, so the 8 rows of the tile use one 32-byte sector per
+//            (h, j) instead of one sector per element (the first version's 8x read amplification).
+//   phase 2: warp = row i, lane = 4 consecutive channels; cells in groups of 4 columns: per head one LDS.128 of
+//            Wp^T and one broadcast LDS.128 of sim feed 16 FMAs.  Then + bias + outer_q[i] + outer_k[j] + prev,
+//            fp32 store (512 B per cell, coalesced), and the RMSNorm of the cell by a warp reduction -> bf16.
 // ---------------------------------------------------------------------------------------------------
-__global__ void pair_combine_kernel(const float* __restrict__ qk, const float* __restrict__ relq,
-                                    const float* __restrict__ relk, const float* __restrict__ Wp,
-                                    const float* __restrict__ bp, const float* __restrict__ outer,
-                                    const float* __restrict__ prev, float* __restrict__ pair, int P, int H, int D, int qk_ld,
-                                    int rel_ld, int rows, int i_off) {
-  // il = local row (this rank owns rows [i_off, i_off + rows) of the P x P pair tensor); i = global row
-  extern __shared__ float sim_s[];  // [32][H + 1]
-  const int jt = blockIdx.x, il = blockIdx.y, b = blockIdx.z;
-  const int i = il + i_off;
-  const int j0 = jt * 32;
-  const int HS = H + 1;
-  for (int idx = threadIdx.x; idx < 32 * H; idx += blockDim.x) {
-    const int jj = idx & 31, h = idx >> 5;
-    const int j = j0 + jj;
-    float s = 0.f;
-    if (j < P) {
-      const long bh = (long)b * H + h;
-      s = qk[(bh * rows + il) * qk_ld + j] +
-          0.5f * (relq[(bh * rows + il) * (long)rel_ld + (P + j - i)] + relk[(bh * P + j) * (long)rel_ld + (P + i - j)]);
+constexpr int kPcI = 8, kPcJ = 32, kPcH = 32, kPcD = 128;
+constexpr int kPcSimI = kPcH * kPcJ + 4;                       // row stride of sim (floats); +4 skews the banks per i
+constexpr int kPcSmem = (kPcH * kPcD + kPcI * kPcSimI) * 4;    // Wp^T [h][c] + sim [i][h][j]
+
+__global__ void __launch_bounds__(256) pair_combine_kernel(const float* __restrict__ qk, const float* __restrict__ relq,
+                                                           const float* __restrict__ relk, const float* __restrict__ Wp,
+                                                           const float* __restrict__ bp, const float* __restrict__ outer,
+                                                           const float* __restrict__ prev, float* __restrict__ pair,
+                                                           const float* __restrict__ nw, const float* __restrict__ nb,
+                                                           __nv_bfloat16* __restrict__ pn, int P, int qk_ld, int rel_ld,
+                                                           int rows, int i_off) {
+  extern __shared__ float pc_smem[];
+  float* wt = pc_smem;                   // [32 h][128 c]
+  float* sim = pc_smem + kPcH * kPcD;    // [8 i][32 h][32 j] (+4 per i)
+  const int j0 = blockIdx.x * kPcJ, il0 = blockIdx.y * kPcI, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  // Wp is [c][h]: transpose into smem once per block (16 KB, L2-resident)
+  for (int idx = tid; idx < kPcH * kPcD; idx += 256) {
+    const int c = idx >> 5, h = idx & 31;
+    wt[h * kPcD + c] = __ldg(Wp + idx);
+  }
+  // pass A: j fastest.  The loads of 8 entries are issued before any is used (the loop is latency-bound otherwise).
+  constexpr int kIters = kPcI * kPcH * kPcJ / 256;   // 32 entries per thread
+#pragma unroll 1
+  for (int it0 = 0; it0 < kIters; it0 += 8) {
+    float va[8], vb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = (it0 + u) * 256 + tid;
+      const int jj = idx & 31, h = (idx >> 5) & 31, ii = idx >> 10;
+      const int il = il0 + ii, j = j0 + jj;
+      va[u] = vb[u] = 0.f;
+      if (il < rows && j < P) {
+        const long row = ((long)b * kPcH + h) * rows + il;
+        va[u] = __ldg(qk + row * qk_ld + j);
+        vb[u] = __ldg(relq + row * (long)rel_ld + (P + j - (il + i_off)));
+      }
     }
-    sim_s[jj * HS + h] = s;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = (it0 + u) * 256 + tid;
+      const int jj = idx & 31, h = (idx >> 5) & 31, ii = idx >> 10;
+      sim[ii * kPcSimI + h * kPcJ + jj] = fmaf(0.5f, vb[u], va[u]);
+    }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float wrow[32];
+  // pass B: i fastest (8 consecutive floats of one relk row per (h, j))
+#pragma unroll 1
+  for (int it0 = 0; it0 < kIters; it0 += 8) {
+    float vk[8];
 #pragma unroll
-    for (int h = 0; h < 32; ++h) wrow[h] = h < H ? __ldg(Wp + c * H + h) : 0.f;
-    const float base = __ldg(bp + c) + outer[((long)b * P + i) * (2 * D) + c];
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = j0 + jj;
-      if (j >= P) break;
-      float acc = base + outer[((long)b * P + j) * (2 * D) + D + c];
+    for (int u = 0; u < 8; ++u) {
+      const int idx = (it0 + u) * 256 + tid;
+      const int ii = idx & 7, jj = (idx >> 3) & 31, h = idx >> 8;
+      const int il = il0 + ii, j = j0 + jj;
+      vk[u] = 0.f;
+      if (il < rows && j < P) vk[u] = __ldg(relk + (((long)b * kPcH + h) * P + j) * (long)rel_ld + (P + (il + i_off) - j));
+    }
 #pragma unroll
-      for (int h = 0; h < 32; ++h) acc = fmaf(wrow[h], sim_s[jj * HS + h], acc);
-      const long o = (((long)b * rows + il) * P + j) * D + c;
-      if (prev) acc += prev[o];
-      pair[o] = acc;
+    for (int u = 0; u < 8; ++u) {
+      const int idx = (it0 + u) * 256 + tid;
+      const int ii = idx & 7, jj = (idx >> 3) & 31, h = idx >> 8;
+      sim[ii * kPcSimI + h * kPcJ + jj] += 0.5f * vk[u];
+    }
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int il = il0 + warp;
+  if (il >= rows) return;
+  const int i = il + i_off;
+  const int c0 = lane * 4;
+  const float4 bias4 = __ldg(reinterpret_cast<const float4*>(bp + c0));
+  const float4 oq = __ldg(reinterpret_cast<const float4*>(outer + ((long)b * P + i) * (2 * kPcD) + c0));
+  const float4 base = make_float4(bias4.x + oq.x, bias4.y + oq.y, bias4.z + oq.z, bias4.w + oq.w);
+  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = w4;
+  if (pn) {
+    w4 = __ldg(reinterpret_cast<const float4*>(nw + c0));
+    b4 = __ldg(reinterpret_cast<const float4*>(nb + c0));
+  }
+  const float* simrow = sim + warp * kPcSimI;
+  for (int jg = 0; jg < kPcJ / 4; ++jg) {
+    const int jb = j0 + jg * 4;
+    if (jb >= P) break;
+    // outer_k / prev are requested here and only added after the head loop, so their latency hides behind it
+    float4 acc[4], pv[4], okv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = jb + q < P ? jb + q : P - 1;   // clamped: columns past P are computed but never stored
+      okv[q] = __ldg(reinterpret_cast<const float4*>(outer + ((long)b * P + j) * (2 * kPcD) + kPcD + c0));
+      acc[q] = base;
+      pv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (prev) pv[q] = __ldg(reinterpret_cast<const float4*>(prev + ((((long)b * rows + il) * P + j) * kPcD) + c0));
+    }
+#pragma unroll 8
+    for (int h = 0; h < kPcH; ++h) {
+      const float4 w = *reinterpret_cast<const float4*>(wt + h * kPcD + c0);
+      const float4 sv = *reinterpret_cast<const float4*>(simrow + h * kPcJ + jg * 4);
+      acc[0].x = fmaf(w.x, sv.x, acc[0].x); acc[0].y = fmaf(w.y, sv.x, acc[0].y); acc[0].z = fmaf(w.z, sv.x, acc[0].z); acc[0].w = fmaf(w.w, sv.x, acc[0].w);
+      acc[1].x = fmaf(w.x, sv.y, acc[1].x); acc[1].y = fmaf(w.y, sv.y, acc[1].y); acc[1].z = fmaf(w.z, sv.y, acc[1].z); acc[1].w = fmaf(w.w, sv.y, acc[1].w);
+      acc[2].x = fmaf(w.x, sv.z, acc[2].x); acc[2].y = fmaf(w.y, sv.z, acc[2].y); acc[2].z = fmaf(w.z, sv.z, acc[2].z); acc[2].w = fmaf(w.w, sv.z, acc[2].w);
+      acc[3].x = fmaf(w.x, sv.w, acc[3].x); acc[3].y = fmaf(w.y, sv.w, acc[3].y); acc[3].z = fmaf(w.z, sv.w, acc[3].z); acc[3].w = fmaf(w.w, sv.w, acc[3].w);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = jb + q;
+      float4 y = make_float4(acc[q].x + (pv[q].x + okv[q].x), acc[q].y + (pv[q].y + okv[q].y), acc[q].z + (pv[q].z + okv[q].z),
+                             acc[q].w + (pv[q].w + okv[q].w));
+      const float ss = warp_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w);   // all lanes take part
+      if (j < P) {
+        const long o = (((long)b * rows + il) * P + j) * kPcD + c0;
+        *reinterpret_cast<float4*>(pair + o) = y;
+        if (pn) {
+          const float inv = rsqrtf(ss * (1.0f / kPcD) + 1e-5f);
+          uint2 pk;
+          pk.x = pack2(y.x * inv * w4.x + b4.x, y.y * inv * w4.y + b4.y);
+          pk.y = pack2(y.z * inv * w4.z + b4.z, y.w * inv * w4.w + b4.w);
+          *reinterpret_cast<uint2*>(pn + o) = pk;
+        }
+      }
     }
   }
 }
@@ -367,11 +537,28 @@ int launch_transpose_bf16(const void* in, void* out, int nb, int R, int C, long 
 }
 
 int launch_pair_bias(const float* pair, const float* scale, const float* shift, const float* W, float* bias, int B,
-                     int rows, int cols, int C, int heads, int device, cudaStream_t st) {
+                     int rows, int cols, int C, int heads, int sets, long set_stride, int device, cudaStream_t st) {
   if (C != 128) return set_error("ag_pair_bias_fwd: built for pair dim 128 (got %d)", C);
-  const long cells = (long)B * rows * cols;
-  pair_bias_kernel<<<grid_for(cells * 32, 256, device), 256, 0, st>>>(pair, scale, shift, W, bias, B, rows, cols, heads);
-  return check_launch("ag_pair_bias_fwd");
+  if (sets != 1 && sets != 2) return set_error("ag_pair_bias_fwd: sets must be 1 or 2 (got %d)", sets);
+  if (!pair || !scale || !shift || !W || !bias) return set_error("ag_pair_bias_fwd: null pointer");
+  const long per_b = (long)rows * cols;
+  const long cells = (long)B * per_b;
+  // fast path: groups of 8 consecutive cells inside one batch element, 16-byte aligned output rows
+  const bool fast = heads == 8 && per_b % 8 == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (set_stride % 4) == 0;
+  const long groups = fast ? cells / 8 : 0;
+  if (groups > 0) {
+    const unsigned grid = grid_for(groups * 32, 256, device, 4);
+    if (sets == 2) pair_bias_kernel<2><<<grid, 256, 0, st>>>(pair, scale, shift, W, bias, groups, per_b, heads, set_stride);
+    else pair_bias_kernel<1><<<grid, 256, 0, st>>>(pair, scale, shift, W, bias, groups, per_b, heads, set_stride);
+    if (int rc = check_launch("ag_pair_bias_fwd")) return rc;
+  }
+  if (groups * 8 < cells) {
+    const long rest = cells - groups * 8;
+    pair_bias_tail_kernel<<<grid_for(rest * 32, 256, device), 256, 0, st>>>(pair, scale, shift, W, bias, groups * 8, cells, per_b,
+                                                                            heads, sets, set_stride);
+    return check_launch("ag_pair_bias_fwd");
+  }
+  return 0;
 }
 
 int launch_pool_rmsnorm(const float* single, const float* w, const float* b, void* x, void* xg, int B, int n, int C,
@@ -383,13 +570,23 @@ int launch_pool_rmsnorm(const float* single, const float* w, const float* b, voi
 }
 
 int launch_pair_combine(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
-                        const float* outer, const float* prev, float* pair, int B, int P, int H, int D, int qk_ld,
-                        int rel_ld, int rows, int i_off, int device, cudaStream_t st) {
-  if (H != 32) return set_error("ag_pair_combine_fwd: built for 32 pair heads (got %d)", H);
+                        const float* outer, const float* prev, float* pair, const float* norm_w, const float* norm_b,
+                        void* pn, int B, int P, int H, int D, int qk_ld, int rel_ld, int rows, int i_off, int device,
+                        cudaStream_t st) {
+  if (H != kPcH || D != kPcD) return set_error("ag_pair_combine_fwd: built for 32 pair heads and pair dim 128 (got %d, %d)", H, D);
   if (qk_ld < P || rel_ld < 2 * P) return set_error("ag_pair_combine_fwd: qk_ld/rel_ld too small");
   if (rows < 1 || i_off < 0 || i_off + rows > P) return set_error("ag_pair_combine_fwd: row range [%d, %d) outside P=%d", i_off, i_off + rows, P);
-  dim3 grid((P + 31) / 32, rows, B);
-  pair_combine_kernel<<<grid, 128, 32 * (H + 1) * sizeof(float), st>>>(qk, relq, relk, Wp, bp, outer, prev, pair, P, H, D, qk_ld, rel_ld, rows, i_off);
+  if (pn && (!norm_w || !norm_b)) return set_error("ag_pair_combine_fwd: the normalised output needs norm_w and norm_b");
+  if (B > 65535 || (rows + kPcI - 1) / kPcI > 65535) return set_error("ag_pair_combine_fwd: grid too large");
+  static thread_local int attr_for = -1;
+  if (attr_for != device) {
+    cudaError_t e = cudaFuncSetAttribute(pair_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcSmem);
+    if (e != cudaSuccess) return set_error("ag_pair_combine_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_for = device;
+  }
+  dim3 grid((P + kPcJ - 1) / kPcJ, (rows + kPcI - 1) / kPcI, B);
+  pair_combine_kernel<<<grid, 256, kPcSmem, st>>>(qk, relq, relk, Wp, bp, outer, prev, pair, norm_w, norm_b,
+                                                  (__nv_bfloat16*)pn, P, qk_ld, rel_ld, rows, i_off);
   return check_launch("ag_pair_combine_fwd");
 }
 

@@ -51,6 +51,7 @@ struct GemmKParams {
   CUtensorMap tmB;
   AgGemmArgs g;
   int n_tile, m_tiles, n_tiles, total_tiles, kblocks;   // m_tiles counts (128 * CG)-row tiles
+  int a_bmask;                                          // 0 when A is shared by every batch (a_bstride == 0), else -1
   unsigned int* err;
 };
 
@@ -172,11 +173,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             if constexpr (CG == 2) {
               // both CTAs' boxes complete on the leader's barrier, which expects the pair's bytes
               if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (kABytes + b_bytes));
-              tma_load_3d_cg2(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b);
+              tma_load_3d_cg2(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b & p.a_bmask);
               tma_load_3d_cg2(sB + stage * kBStage, &p.tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
-              tma_load_3d(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b);
+              tma_load_3d(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b & p.a_bmask);
               tma_load_3d(sB + stage * kBStage, &p.tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -447,8 +448,10 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   p.err = device_error_word(device);
 
   {
-    uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.a_rows, (uint64_t)a.batch};
-    uint64_t strides[2] = {(uint64_t)a.a_ld * 2, (uint64_t)(a.batch > 1 ? a.a_bstride : (int64_t)a.a_ld * a.a_rows) * 2};
+    const bool a_shared = a.batch > 1 && a.a_bstride == 0;   // one A for every batch (e.g. a weight as the row operand)
+    p.a_bmask = a_shared ? 0 : -1;
+    uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.a_rows, (uint64_t)(a_shared ? 1 : a.batch)};
+    uint64_t strides[2] = {(uint64_t)a.a_ld * 2, (uint64_t)(a.batch > 1 && !a_shared ? a.a_bstride : (int64_t)a.a_ld * a.a_rows) * 2};
     uint32_t box[3] = {kBlockK, kBlockM, 1};
     if (int rc = make_tensor_map_bf16(&p.tmA, a.A, 3, dims, strides, box)) return rc;
   }

@@ -33,12 +33,13 @@ int launch_qkv_post(const float* qkv, void* Q, void* K, void* V, const float* co
 int launch_transpose_bf16(const void* in, void* out, int nb, int R, int C, long in_bs, int in_ld, long out_bs,
                           int out_ld, int device, cudaStream_t st);
 int launch_pair_bias(const float* pair, const float* scale, const float* shift, const float* W, float* bias, int B,
-                     int rows, int cols, int C, int heads, int device, cudaStream_t st);
+                     int rows, int cols, int C, int heads, int sets, long set_stride, int device, cudaStream_t st);
 int launch_pool_rmsnorm(const float* single, const float* w, const float* b, void* x, void* xg, int B, int n, int C,
                         int pool, int device, cudaStream_t st);
 int launch_pair_combine(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
-                        const float* outer, const float* prev, float* pair, int B, int P, int H, int D, int qk_ld,
-                        int rel_ld, int rows, int i_off, int device, cudaStream_t st);
+                        const float* outer, const float* prev, float* pair, const float* norm_w, const float* norm_b,
+                        void* pn, int B, int P, int H, int D, int qk_ld, int rel_ld, int rows, int i_off, int device,
+                        cudaStream_t st);
 int launch_rmsnorm(const float* x, const float* w, const float* b, void* out, long rows, int C, int device,
                    cudaStream_t st);
 int launch_add_embed_norm(const float* x, const float* emb, const float* scale, const float* shift, float* single,

@@ -108,7 +108,10 @@ def gemm(
     N = W.shape[1]
     _require(W.shape[2] == K, f"K mismatch: A {tuple(A.shape)} W {tuple(W.shape)}")
     taps = 1 if w_batched else W.shape[0]
+    a_shared = False
     if w_batched:
+        if batch == 1 and W.shape[0] > 1:   # one A (e.g. a weight matrix as the row operand) against every W[b]
+            a_shared, batch = True, W.shape[0]
         _require(W.shape[0] == batch, "batched W needs W.shape[0] == batch")
     if M is None:
         M = a_rows - 2 * a_row0
@@ -120,7 +123,7 @@ def gemm(
 
     g = AgGemmArgs()
     g.A = A.data_ptr()
-    g.a_bstride = A.stride(0) if batch > 1 else A.stride(1) * a_rows  # stride of a size-1 dim is arbitrary
+    g.a_bstride = 0 if a_shared else (A.stride(0) if batch > 1 else A.stride(1) * a_rows)  # stride of a size-1 dim is arbitrary
     g.a_ld = A.stride(1)
     g.a_rows = a_rows
     g.a_row0 = a_row0
@@ -207,6 +210,9 @@ def attention(
     softcap: float = 5.0,
     out_bias: Optional[torch.Tensor] = None,
     res: Optional[torch.Tensor] = None,
+    norm_w: Optional[torch.Tensor] = None,
+    norm_b: Optional[torch.Tensor] = None,
+    norm_out: Optional[torch.Tensor] = None,
 ) -> None:
     """ag_attention_fwd.  Q [B, H, n_q, d], K [B, Hk, n_k, d], Vt [B, Hk, dv, n_k(+pad)] (bf16 views, last dim
     contiguous), out [B, H, n_q, dv] (bf16 or fp32 view).  n_k is taken from K."""
@@ -241,6 +247,13 @@ def attention(
     if res is not None:
         _require(res.dtype == torch.float32 and res.shape == out.shape and res.stride() == out.stride(), "res must match out's layout")
     a.res = _ptr(res)
+    if norm_out is not None:
+        _require(out.dtype == torch.float32 and norm_out.dtype == torch.bfloat16 and norm_out.shape == out.shape and
+                 norm_out.stride() == out.stride(), "norm_out must be bf16 with out's layout (fp32 out only)")
+        _f32(norm_w, "norm_w")
+        _f32(norm_b, "norm_b")
+        _require(norm_w is not None and norm_b is not None and norm_w.numel() == dv and norm_b.numel() == dv, "norm_w/norm_b must be fp32 [dv]")
+    a.norm_w, a.norm_b, a.norm_out = _ptr(norm_w), _ptr(norm_b), _ptr(norm_out)
     _lib.check(lib.ag_attention_fwd(C.byref(a), _dev(Q), _stream()))
 
 
@@ -273,12 +286,18 @@ def transpose_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
 
 
 def pair_bias(pair, scale, shift, W, bias_out) -> None:
+    """ag_pair_bias_fwd.  One layer: scale/shift [C], W [heads, C], bias_out [B, heads, rows, cols].  Two layers sharing
+    the pair tensor: scale/shift [2, C], W [2, heads, C], bias_out [2, B, heads, rows, cols]."""
     B, rows, cols, Cc = pair.shape
     for t, nm in ((pair, "pair"), (scale, "scale"), (shift, "shift"), (W, "W"), (bias_out, "bias_out")):
         _f32(t, nm)
-    heads = W.shape[0]
-    _require(tuple(bias_out.shape) == (B, heads, rows, cols), "bias_out must be [B, heads, rows, cols]")
-    _lib.check(_lib.load().ag_pair_bias_fwd(pair.data_ptr(), scale.data_ptr(), shift.data_ptr(), W.data_ptr(), bias_out.data_ptr(), B, rows, cols, Cc, heads, _dev(pair), _stream()))
+    sets = W.shape[0] if W.dim() == 3 else 1
+    heads = W.shape[-2]
+    _require(scale.numel() == sets * Cc and shift.numel() == sets * Cc and W.shape[-1] == Cc, "scale/shift/W shape mismatch")
+    want = (sets, B, heads, rows, cols) if W.dim() == 3 else (B, heads, rows, cols)
+    _require(tuple(bias_out.shape) == want, f"bias_out must be {want}")
+    _lib.check(_lib.load().ag_pair_bias_fwd(pair.data_ptr(), scale.data_ptr(), shift.data_ptr(), W.data_ptr(), bias_out.data_ptr(), B, rows,
+                                            cols, Cc, heads, sets, B * heads * rows * cols, _dev(pair), _stream()))
 
 
 def pool_rmsnorm(single, w, b, x_out, xg_out, pool: int) -> None:
@@ -290,17 +309,23 @@ def pool_rmsnorm(single, w, b, x_out, xg_out, pool: int) -> None:
     _lib.check(_lib.load().ag_pool_rmsnorm_fwd(single.data_ptr(), w.data_ptr(), b.data_ptr(), x_out.data_ptr(), xg_out.data_ptr(), B, n, Cc, pool, _dev(single), _stream()))
 
 
-def pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair_out, P: int, i_off: int = 0) -> None:
-    """qk/relq/prev/pair_out hold this rank's rows [i_off, i_off+rows); relk and outer hold all P rows."""
+def pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair_out, P: int, i_off: int = 0, norm_w=None, norm_b=None, norm_out=None) -> None:
+    """qk/relq/prev/pair_out hold this rank's rows [i_off, i_off+rows); relk and outer hold all P rows.
+    norm_out (bf16, pair_out's shape) optionally receives RMSNormWithBias(pair_out) with (norm_w, norm_b)."""
     B, H, rows = qk.shape[0], qk.shape[1], qk.shape[2]
     D = Wp.shape[0]
-    for t, nm in ((qk, "qk"), (relq, "relq"), (relk, "relk"), (Wp, "Wp"), (bp, "bp"), (outer, "outer"), (prev, "prev"), (pair_out, "pair_out")):
+    for t, nm in ((qk, "qk"), (relq, "relq"), (relk, "relk"), (Wp, "Wp"), (bp, "bp"), (outer, "outer"), (prev, "prev"), (pair_out, "pair_out"),
+                  (norm_w, "norm_w"), (norm_b, "norm_b")):
         _f32(t, nm)
     _require(tuple(relq.shape[:3]) == (B, H, rows) and tuple(relk.shape[:3]) == (B, H, P) and relk.shape[3] == relq.shape[3], "relq [B,H,rows,ld], relk [B,H,P,ld]")
     _require(tuple(outer.shape) == (B, P, 2 * D) and tuple(pair_out.shape) == (B, rows, P, D), "outer/pair_out shape mismatch")
     _require(prev is None or prev.shape == pair_out.shape, "prev must match pair_out")
+    if norm_out is not None:
+        _require(norm_out.dtype == torch.bfloat16 and norm_out.is_contiguous() and norm_out.numel() == pair_out.numel(), "norm_out must be contiguous bf16 of pair_out's size")
+        _require(norm_w is not None and norm_b is not None and norm_w.numel() == D and norm_b.numel() == D, "norm_w/norm_b must be fp32 [D]")
     _lib.check(_lib.load().ag_pair_combine_fwd(qk.data_ptr(), relq.data_ptr(), relk.data_ptr(), Wp.data_ptr(), bp.data_ptr(), outer.data_ptr(),
-                                               _ptr(prev), pair_out.data_ptr(), B, P, H, D, qk.shape[3], relq.shape[3], rows, i_off, _dev(qk), _stream()))
+                                               _ptr(prev), pair_out.data_ptr(), _ptr(norm_w), _ptr(norm_b), _ptr(norm_out), B, P, H, D, qk.shape[3],
+                                               relq.shape[3], rows, i_off, _dev(qk), _stream()))
 
 
 def rmsnorm(x, w, b, out) -> None:

@@ -133,6 +133,17 @@ class TrunkEngine:
                 L["pff"] = dict(nw=vec(pff_w.pre_rmsnorm.weight), nb=vec(pff_w.pre_rmsnorm.bias), W1=wlin(pff_w.block[0]),
                                 b1=vec(pff_w.block[0].bias), W2=wlin(pff_w.block[3]), b2=vec(pff_w.block[3].bias))
             layers.append(L)
+        # to_attn_bias of a pair-updating layer and of the following layer(s) that reuse the same pair tensor are
+        # projected in one pass over it (ag_pair_bias_fwd takes up to two parameter sets)
+        for li, L in enumerate(layers):
+            if "s2p" in L or li == 0:
+                grp = [li]
+                if li + 1 < len(layers) and "s2p" not in layers[li + 1]:
+                    grp.append(li + 1)
+                ats = [layers[j]["attn"] for j in grp]
+                L["bias_group"] = dict(layers=grp, s=torch.stack([a["ab_s"] for a in ats]).contiguous(),
+                                       t=torch.stack([a["ab_t"] for a in ats]).contiguous(),
+                                       W=torch.stack([a["ab_W"] for a in ats]).contiguous())
         P["layers"] = layers
         P["inv_freq"] = tw.rotary_emb.inv_freq.detach().float().cpu()
 
@@ -267,27 +278,28 @@ class TrunkEngine:
             ops.gemm(qb, R, w_batched=True, n_pad=N2, out=relq[b])          # (q_i + bq) . R[p]    (AG:843)
             ops.gemm(kb, R, w_batched=True, n_pad=N2, out=relk[b])          # (k_j + bk) . R[p]    (AG:844)
         new_pair = torch.empty(B, Pl, Pn, dp, **f32)
-        ops.pair_combine(qk_out, relq, relk, sp["Wp"], sp["bp"], outer, pair, new_pair, P=Pn, i_off=i0)
+        cells = B * Pl * Pn
+        pn = torch.empty(1, cells, dp, **bf)   # RMSNormWithBias(pair): the row attention's pre-norm, fused into the combine
+        ops.pair_combine(qk_out, relq, relk, sp["Wp"], sp["bp"], outer, pair, new_pair, P=Pn, i_off=i0,
+                         norm_w=pa["nw"], norm_b=pa["nb"], norm_out=pn)
         pair = new_pair
         del qk_out, relq, relk, qk_plain, qk_bias
         self._note(f"tower.layer{li}.pair_s2p", pair)
         # --- row attention (AG:1021): attends over the second index, so a row shard is self-contained ---
-        cells = B * Pl * Pn
-        pn = torch.empty(1, cells, dp, **bf)
-        ops.rmsnorm(pair, pa["nw"], pa["nb"], pn)
         qkp = torch.empty(1, cells, 2 * dp, **bf)
         ops.gemm(pn, pa["Wqk"], actA=Act(qkp))
-        vp = torch.empty(1, cells, dp, **bf)
-        ops.gemm(pn, pa["Wv"], actA=Act(vp))
-        Pk = _round_up(Pn, 8)
-        vpt = torch.zeros(B * Pl, dp, Pk, **bf) if Pk != Pn else torch.empty(B * Pl, dp, Pk, **bf)
-        ops.transpose_bf16(vp.view(B * Pl, Pn, dp), vpt)
+        # V^T straight out of the GEMM: with Wv as the row operand (shared by every pair row) and the normalised pair
+        # row as the "weight" of batch i, out[i] = Wv . pn[i]^T = [dp, Pn] with keys contiguous — the layout the
+        # attention's P.V operand wants; no transpose pass.  (to_v's bias is added after the softmax, see out_bias.)
+        Pk = _round_up(Pn, 16)
+        vpt = torch.empty(B * Pl, dp, Pk, **bf)
+        ops.gemm(pa["Wv"], pn.view(B * Pl, Pn, dp), w_batched=True, n_pad=Pk, actA=Act(vpt))
         q4 = qkp.view(B, Pl, Pn, 2 * dp)
+        # the epilogue also emits RMSNormWithBias(pair) for the pair feed-forward (its pre-norm, AG:972-975) into pn
         ops.attention(q4[..., :dp], q4[..., dp:], vpt.view(B, Pl, dp, Pk), pair, mode=1, scale=pa["scale"],
-                      out_bias=pa["bv"], res=pair)
+                      out_bias=pa["bv"], res=pair, norm_w=pf["nw"], norm_b=pf["nb"], norm_out=pn.view(B, Pl, Pn, dp))
         self._note(f"tower.layer{li}.pair_attn", pair)
         # --- pair feed-forward (AG:1022) ---
-        ops.rmsnorm(pair, pf["nw"], pf["nb"], pn)
         hid = torch.empty(1, cells, pf["W1"].shape[1], **bf)
         ops.gemm(pn, pf["W1"], pre_shift=pf["b1"], relu=True, actA=Act(hid))
         pflat = pair.view(1, cells, dp)
@@ -314,6 +326,7 @@ class TrunkEngine:
         ops.add_embed_norm(x, org_embed.to(torch.float32).contiguous(), s0, t0, single, a)
         cos_t, sin_t = self.rope_tables(n, dev, offset=plan.tok_off if sharded else 0)
         pair = None
+        bias_of = {}
         a_ff = torch.empty(B, n, D, **bf)
         for li, L in enumerate(layers):
             if "s2p" in L:
@@ -332,8 +345,18 @@ class TrunkEngine:
             nk = _round_up(n_all, 8)
             Vt = torch.empty(B, dv, nk, **bf)
             ops.transpose_bf16(V, Vt)
-            bias = torch.empty(B, Hh, pair.shape[1], pair.shape[2], **f32)
-            ops.pair_bias(pair, at["ab_s"], at["ab_t"], at["ab_W"], bias)
+            if "bias_group" in L:
+                bg = L["bias_group"]
+                bias_sets = torch.empty(len(bg["layers"]), B, Hh, pair.shape[1], pair.shape[2], **f32)
+                if len(bg["layers"]) == 2:
+                    ops.pair_bias(pair, bg["s"], bg["t"], bg["W"], bias_sets)
+                else:
+                    ops.pair_bias(pair, bg["s"][0], bg["t"][0], bg["W"][0], bias_sets[0])
+                bias_of = {j: bias_sets[k] for k, j in enumerate(bg["layers"])}
+            elif li not in bias_of:   # a layer without its own pair block that follows another such layer
+                bias_of = {li: torch.empty(B, Hh, pair.shape[1], pair.shape[2], **f32)}
+                ops.pair_bias(pair, at["ab_s"], at["ab_t"], at["ab_W"], bias_of[li])
+            bias = bias_of[li]
             O = torch.empty(B, n, Hh * dv, **bf)
             ops.attention(Q.view(B, n, Hh, d).permute(0, 2, 1, 3), K.unsqueeze(1), Vt.view(B, 1, dv, nk),
                           O.view(B, n, Hh, dv).permute(0, 2, 1, 3), mode=0, scale=at["scale"], bias=bias, softcap=at["softcap"])

@@ -72,7 +72,7 @@ typedef struct AgEpiOut {
  */
 typedef struct AgGemmArgs {
   const void* A;      /* bf16 */
-  int64_t a_bstride;  /* elements between batches */
+  int64_t a_bstride;  /* elements between batches; 0 with batch > 1 = ONE A shared by every batch */
   int32_t a_ld;       /* elements between rows (multiple of 8) */
   int32_t a_rows;     /* rows per batch present in the buffer (incl. halo rows) */
   int32_t a_row0;     /* buffer row of logical row 0 */
@@ -138,6 +138,11 @@ typedef struct AgAttnArgs {
   const float* res;      /* fp32, same addressing as out, or NULL (fp32 out only; may alias out) */
   int32_t bias_rows;     /* bias rows (>= n_q/16); 0 = bias_p.  bias is [batch][heads][bias_rows][bias_p] */
   int32_t reserved1;
+  /* optional (fp32 out, dv == 128): RMSNormWithBias (AG:400-405) of each finished output row, bf16, addressed like out —
+   * the pre-norm of the pair feed-forward that follows the row attention (NormWrapper, AG:972-975) */
+  const float* norm_w;   /* [dv] or NULL */
+  const float* norm_b;   /* [dv] */
+  void* norm_out;        /* bf16 or NULL */
 } AgAttnArgs;
 
 int ag_attention_fwd(const AgAttnArgs* args, int device, void* stream);
@@ -162,10 +167,13 @@ int ag_qkv_post_fwd(const float* qkv, void* Q, void* K, void* V, const float* co
 int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t C, int64_t in_bstride,
                       int32_t in_ld, int64_t out_bstride, int32_t out_ld, int device, void* stream);
 
-/* to_attn_bias (AG:688-693): bias[b][g][i][j] = sum_c W[g][c] * gelu_erf(pair[b][i][j][c]*scale[c] + shift[c]);
- * pair is [B][rows][cols][C] (rows < cols for a sequence-parallel row shard), bias [B][heads][rows][cols] */
+/* to_attn_bias (AG:688-693) of `sets` (1 or 2) attention layers that read the same pair tensor, in one pass over it:
+ * bias[s][b][g][i][j] = sum_c W[s][g][c] * gelu_erf(pair[b][i][j][c]*scale[s][c] + shift[s][c]);
+ * pair is [B][rows][cols][C] (rows < cols for a sequence-parallel row shard); scale/shift [sets][C]; W [sets][heads][C];
+ * bias holds `sets` tensors [B][heads][rows][cols] that are `set_stride` floats apart */
 int ag_pair_bias_fwd(const float* pair, const float* scale, const float* shift, const float* W, float* bias,
-                     int32_t B, int32_t rows, int32_t cols, int32_t C, int32_t heads, int device, void* stream);
+                     int32_t B, int32_t rows, int32_t cols, int32_t C, int32_t heads, int32_t sets, int64_t set_stride,
+                     int device, void* stream);
 
 /* SingleToPairwise prologue (AG:828-829, 852): mean over `pool` tokens -> RMSNormWithBias ->
  * x_bf16 [B][P][C] and gelu_erf(x) bf16 [B][P][C] */
@@ -176,10 +184,13 @@ int ag_pool_rmsnorm_fwd(const float* single, const float* w, const float* b, voi
  * outer[b][j][D:] (+ prev), with sim[..h] = qk[b][h][i][j] + 0.5*(relq[b][h][i][P+j-i] + relk[b][h][j][P+i-j]);
  * qk rows are qk_ld floats apart, relq/relk rows rel_ld floats apart (padded to the GEMM's N multiple of 16).
  * Sequence-parallel row shard: this call produces global rows i in [i_off, i_off+rows); qk, relq, prev and pair hold
- * only those rows ([B][H][rows][..] / [B][rows][P][D]); relk and outer hold all P rows. */
+ * only those rows ([B][H][rows][..] / [B][rows][P][D]); relk and outer hold all P rows.
+ * If pair_norm_bf16 is non-null it also receives RMSNormWithBias(pair) (AG:400-405 with norm_w/norm_b [D]) in bf16 —
+ * the pre-norm of the PairwiseRowAttention that consumes the result (NormWrapper, AG:974). */
 int ag_pair_combine_fwd(const float* qk, const float* relq, const float* relk, const float* Wp, const float* bp,
-                        const float* outer, const float* prev, float* pair, int32_t B, int32_t P, int32_t H,
-                        int32_t D, int32_t qk_ld, int32_t rel_ld, int32_t rows, int32_t i_off, int device, void* stream);
+                        const float* outer, const float* prev, float* pair, const float* norm_w, const float* norm_b,
+                        void* pair_norm_bf16, int32_t B, int32_t P, int32_t H, int32_t D, int32_t qk_ld, int32_t rel_ld,
+                        int32_t rows, int32_t i_off, int device, void* stream);
 
 /* RMSNormWithBias over the last dim (AG:400-405): fp32 [rows][C] -> bf16 [rows][C] */
 int ag_rmsnorm_fwd(const float* x, const float* w, const float* b, void* out_bf16, int64_t rows, int32_t C,

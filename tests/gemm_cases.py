@@ -39,7 +39,7 @@ def ref_acc(A, W, M, a_row0, w_batched):
     return acc
 
 
-def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogue="plain", seed=0, strided=False, cta_group=0):
+def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogue="plain", seed=0, strided=False, cta_group=0, a_shared=False):
     """Returns dict(name, ok, max_err, details...). Tolerance: fp32-accumulate of bf16 products, so the only
     error is summation order -> 2e-3 relative to the output scale is generous and still catches any
     descriptor/layout bug (those give O(1) errors)."""
@@ -53,10 +53,11 @@ def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogu
         W_store = (torch.randn(N, batch, K, generator=gen) * 0.5).to(dev).bfloat16()
         W = W_store.permute(1, 0, 2)
     else:
-        A = (torch.randn(batch, rows, K, generator=gen) * 0.5).to(dev).bfloat16()
+        A = (torch.randn(1 if a_shared else batch, rows, K, generator=gen) * 0.5).to(dev).bfloat16()
         nz = batch if w_batched else taps
         W = (torch.randn(nz, N, K, generator=gen) / math.sqrt(K * taps)).to(dev).bfloat16()
-    acc = ref_acc(A, W, M, a_row0, w_batched)
+    # a_shared: ONE A for every batch of a batched W (the pair row attention's V^T = Wv . pn[i]^T)
+    acc = ref_acc(A.expand(batch, -1, -1) if a_shared else A, W, M, a_row0, w_batched)
 
     res = {}
     kw = {}
@@ -146,4 +147,5 @@ CASES = [
     dict(name="pair_n176_full_epi", batch=2, M=768, K=320, N=1408, epilogue="full"),
     dict(name="pair_deep_k", batch=1, M=512, K=3072, N=1536),
     dict(name="pair_n16", batch=1, M=4096, K=128, N=16),
+    dict(name="shared_a_batched_w", batch=6, M=128, K=128, N=48, w_batched=True, a_shared=True, epilogue="relu_bf16"),
 ]

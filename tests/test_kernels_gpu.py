@@ -70,6 +70,15 @@ def test_attention_pair_rows(B, P):
     ops.attention(xc[..., :D], xc[..., D:], vt.to(DEV), pair, mode=1, scale=D ** -0.5, out_bias=bv.to(DEV), res=pair)
     torch.cuda.synchronize()
     assert rel_err(pair, want) < 1e-2  # P is bf16 (2^-9); outputs fp32
+    # fused pre-norm of the pair feed-forward: bf16 RMSNormWithBias of the fp32 rows the same launch wrote
+    nsd = {"n.weight": 1 + 0.2 * g(D, seed=9), "n.bias": 0.1 * g(D, seed=10)}
+    pair2 = res.to(DEV).contiguous()
+    pn = torch.zeros(B, P, P, D, dtype=torch.bfloat16, device=DEV)
+    ops.attention(xc[..., :D], xc[..., D:], vt.to(DEV), pair2, mode=1, scale=D ** -0.5, out_bias=bv.to(DEV), res=pair2,
+                  norm_w=nsd["n.weight"].to(DEV), norm_b=nsd["n.bias"].to(DEV), norm_out=pn)
+    torch.cuda.synchronize()
+    assert torch.equal(pair2, pair)
+    assert rel_err(pn, O.rms_norm_bias(nsd, "n.", pair.float().cpu())) < 6e-3
 
 
 # ------------------------------------------------------------------------------------------------ small kernels
@@ -122,17 +131,29 @@ def test_transpose_bf16():
     assert torch.all(out[:, :, 70:] == 0)
 
 
-def test_pair_bias_projection():
-    B, P = 2, 9
-    pair = g(B, P, P, 128, seed=2, scale=3.0)
-    sd = {"to_attn_bias.0.gamma": 1 + 0.2 * g(128, seed=3), "to_attn_bias.0.beta": 0.1 * g(128, seed=4),
-          "to_attn_bias.0.running_var": torch.rand(128) + 0.5, "to_attn_bias.2.weight": g(8, 128, seed=5, scale=0.1)}
-    want = O.attention_bias(sd, "", pair)
-    s, t = O.batch_rms_affine(sd, "to_attn_bias.0.")
-    out = torch.empty(B, 8, P, P, device=DEV)
+@pytest.mark.parametrize("B,rows,cols", [(2, 9, 9), (1, 8, 24), (2, 16, 64)])
+@pytest.mark.parametrize("sets", [1, 2])
+def test_pair_bias_projection(B, rows, cols, sets):
+    """One and two parameter sets (two attention layers sharing the pair tensor); shapes that take the 8-cell fast
+    path (rows*cols % 8 == 0), the per-cell tail path (9x9) and a row shard (rows < cols)."""
+    pair = g(B, rows, cols, 128, seed=2, scale=3.0)
     c = lambda t: t.to(DEV).contiguous()
-    ops.pair_bias(c(pair), c(s), c(t), c(sd["to_attn_bias.2.weight"]), out)
-    assert rel_err(out, want) < 1e-5
+    S, T, W, want = [], [], [], []
+    for k in range(sets):
+        sd = {"to_attn_bias.0.gamma": 1 + 0.2 * g(128, seed=3 + 10 * k), "to_attn_bias.0.beta": 0.1 * g(128, seed=4 + 10 * k),
+              "to_attn_bias.0.running_var": torch.rand(128, generator=torch.Generator().manual_seed(k)) + 0.5,
+              "to_attn_bias.2.weight": g(8, 128, seed=5 + 10 * k, scale=0.1)}
+        want.append(O.attention_bias(sd, "", pair).reshape(B, 8, rows, cols))
+        s_, t_ = O.batch_rms_affine(sd, "to_attn_bias.0.")
+        S.append(s_), T.append(t_), W.append(sd["to_attn_bias.2.weight"])
+    if sets == 1:
+        out = torch.full((B, 8, rows, cols), float("nan"), device=DEV)
+        ops.pair_bias(c(pair), c(S[0]), c(T[0]), c(W[0]), out)
+        assert rel_err(out, want[0]) < 1e-5
+    else:
+        out = torch.full((2, B, 8, rows, cols), float("nan"), device=DEV)
+        ops.pair_bias(c(pair), c(torch.stack(S)), c(torch.stack(T)), c(torch.stack(W)), out)
+        assert rel_err(out[0], want[0]) < 1e-5 and rel_err(out[1], want[1]) < 1e-5
 
 
 def test_pool_rmsnorm():
@@ -170,6 +191,19 @@ def test_pair_combine(P):
     assert rel_err(out, want) < 1e-5
     ops.pair_combine(c(qk), c(relq), c(relk), c(Wp), c(bp), c(outer), None, out, P=P)
     assert rel_err(out, want - prev) < 1e-5
+    # fused pre-norm of the row attention (RMSNormWithBias) and a row shard [i_off, i_off + rows)
+    nsd = {"n.weight": 1 + 0.2 * g(D, seed=8), "n.bias": 0.1 * g(D, seed=9)}
+    pn = torch.zeros(B, P, P, D, dtype=torch.bfloat16, device=DEV)
+    ops.pair_combine(c(qk), c(relq), c(relk), c(Wp), c(bp), c(outer), c(prev), out, P=P, norm_w=c(nsd["n.weight"]),
+                     norm_b=c(nsd["n.bias"]), norm_out=pn)
+    assert rel_err(out, want) < 1e-5
+    assert rel_err(pn, O.rms_norm_bias(nsd, "n.", want)) < 6e-3
+    if P > 8:
+        i0, rows = 5, 11
+        out_s = torch.empty(B, rows, P, D, device=DEV)
+        ops.pair_combine(c(qk[:, :, i0:i0 + rows]), c(relq[:, :, i0:i0 + rows]), c(relk), c(Wp), c(bp), c(outer), c(prev[:, i0:i0 + rows]),
+                         out_s, P=P, i_off=i0)
+        assert rel_err(out_s, want[:, i0:i0 + rows]) < 1e-5
 
 
 def test_rmsnorm_rows():
