@@ -76,7 +76,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int kPolyOf8>
+// kSplit = 2 (mode 0 only): a cluster of two CTAs shares one (batch, head, query tile); each takes half of the key
+// blocks.  Because soft-capped logits need no running max, the halves combine by plain addition: the second CTA
+// ships its unnormalised O (fp32) and row sums into the first CTA's (by then idle) K/V shared memory over DSMEM.
+// Used when the grid would otherwise leave SMs idle (a sequence-parallel rank has only n_q / 128 x heads tiles) or
+// to cut the last partial wave.
+template <int kPolyOf8, int kSplit>
 __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_constant__ AttnKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const AgAttnArgs& a = p.a;
@@ -99,14 +104,20 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int qt = blockIdx.x % p.q_tiles;
-  const int h = (blockIdx.x / p.q_tiles) % a.heads;
-  const int b = blockIdx.x / (p.q_tiles * a.heads);
+  const int tile = kSplit == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const uint32_t crank = kSplit == 2 ? cluster_ctarank() : 0u;
+  const int qt = tile % p.q_tiles;
+  const int h = (tile / p.q_tiles) % a.heads;
+  const int b = tile / (p.q_tiles * a.heads);
   const int hk = a.kv_heads == 1 ? 0 : h;
   const int q0 = qt * kAttBM;
   const int dv = a.dv;
-  const int npre = a.mode == 1 ? p.nblk : 0;
-  const int nsteps = npre + p.nblk;
+  // this CTA's key blocks [kb0, kb0 + nblk)
+  const int nblk_lo = kSplit == 2 ? (p.nblk + 1) / 2 : p.nblk;
+  const int kb0 = crank == 0 ? 0 : nblk_lo;
+  const int nblk = crank == 0 ? nblk_lo : p.nblk - nblk_lo;
+  const int npre = a.mode == 1 ? nblk : 0;
+  const int nsteps = npre + nblk;
   const uint32_t v_bytes = (uint32_t)dv * kAttBN * 2;
 
   if (warp == 0 && lane == 0) {
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     // ---------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       for (int s = 0; s < nsteps; ++s) {
-        const int kb = s < npre ? s : s - npre;
+        const int kb = kb0 + (s < npre ? s : s - npre);
         const int st = s & 1;
         mbar_wait(&k_empty[st], ((s >> 1) & 1) ^ 1u, 0x110u + st, p.err);
         mbar_arrive_expect_tx(&k_full[st], kAttKBytes);
@@ -255,15 +266,15 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     // bias scalars of the NEXT key block are requested one step ahead, so their global-load latency (the largest
     // stall of the first version, ncu: long_scoreboard on the first use) hides behind a whole block of math
     float nb0 = 0.f, nb1 = 0.f;
-    if (a.mode == 0) {
-      const int pc = cq * 2;
+    if (a.mode == 0 && nsteps > 0) {
+      const int pc = kb0 * 8 + cq * 2;
       if (pc < a.bias_p) nb0 = __ldg(bias_row + pc);
       if (pc + 1 < a.bias_p) nb1 = __ldg(bias_row + pc + 1);
     }
 
     for (int s = 0; s < nsteps; ++s) {
       const int st = s & 1;
-      const int kb = s < npre ? s : s - npre;
+      const int kb = kb0 + (s < npre ? s : s - npre);
       const int key0 = kb * kAttBN + cq * 32;
       if (s == npre && npre > 0) {
         // mode 1: pass 1 done -> combine the four column quarters' row maxima before any exp
@@ -332,9 +343,31 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     // ---- epilogue: O / rowsum (+ bias + residual); each column quarter writes dv/4 of the columns ----
     xch[cq * 128 + lrow] = (rsum[0] + rsum[1]) + (rsum[2] + rsum[3]);
     asm volatile("bar.sync 1, 512;" ::: "memory");
-    const float inv = 1.0f / ((xch[lrow] + xch[128 + lrow]) + (xch[256 + lrow] + xch[384 + lrow]));
+    float rtot = (xch[lrow] + xch[128 + lrow]) + (xch[256 + lrow] + xch[384 + lrow]);
     mbar_wait(o_full, 0, 0x190u, p.err);
     tc_fence_after();
+    float4* land = reinterpret_cast<float4*>(smem);           // [dv/16 float4 slots][512 threads] + row sums
+    const int tsoft = threadIdx.x - 64;
+    if constexpr (kSplit == 2) {
+      cluster_sync_all();                                      // #1: both CTAs' MMAs are complete, K/V smem is idle
+      if (crank == 1) {
+        const uint32_t land_remote = mapa_u32(smem_u32(land), 0u);
+#pragma unroll 1
+        for (int c16 = 0; c16 < dv / 64; ++c16) {
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_O + lane_off + (uint32_t)(cq * (dv / 4) + 16 * c16), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_cluster_v4(land_remote + (uint32_t)(((c16 * 4 + q) * 512 + tsoft) * 16), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        }
+        if (cq == 0) st_cluster_f32(land_remote + (uint32_t)((dv / 16) * 512 * 16 + lrow * 4), rtot);
+      }
+      cluster_sync_all();                                      // #2: the partner's partial results have landed
+      if (crank == 0) rtot += reinterpret_cast<const float*>(land + (dv / 16) * 512)[lrow];
+    }
+    if (crank == 0) {   // (kSplit == 1: always) this CTA writes the tile
+    const float inv = 1.0f / rtot;
     const long obase = (long)b * a.out_bstride + (long)h * a.out_hstride + (long)row * a.out_ld;
     const int cbeg = cq * (dv / 4), cend = cbeg + dv / 4;
     if (a.norm_out != nullptr) {
@@ -393,6 +426,17 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       uint32_t r[16];
       tmem_ld_32x16(tmem_O + lane_off + (uint32_t)c0, r);
       tmem_ld_wait();
+      if constexpr (kSplit == 2) {
+        const int c16 = (c0 - cbeg) >> 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 o2 = land[(c16 * 4 + q) * 512 + tsoft];
+          r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + o2.x);
+          r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + o2.y);
+          r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + o2.z);
+          r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + o2.w);
+        }
+      }
       if (row < a.n_q) {
         if (a.out_dtype == 0) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + c0;
@@ -429,7 +473,14 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       }
     }
     }
+    }
     tc_fence_before();
+  }
+  if constexpr (kSplit == 2) {
+    if (warp < 2) {          // the TMA / MMA warps take part in the two cluster barriers of the combine
+      cluster_sync_all();
+      cluster_sync_all();
+    }
   }
 
   __syncthreads();
@@ -489,25 +540,49 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
     uint32_t box[4] = {64, (uint32_t)a.dv, 1, 1};
     if (int rc = make_tensor_map_bf16(&p.tmV, a.Vt, 4, dims, str, box)) return rc;
   }
+  // key split: two CTAs per tile when that shortens the schedule (waves x blocks per CTA; the DSMEM combine costs about
+  // 6 blocks' worth: measured 0.371 -> 0.385 ms at 512 tiles x 64 blocks, 0.098 -> 0.063 ms at 64 tiles x 64 blocks)
+  const long tiles = (long)p.q_tiles * a.heads * a.batch;
+  if (tiles > 1073741823L) return set_error("ag_attention_fwd: grid too large");
+  const int sms = sm_count(device);
+  int split = 1;
+  if (a.mode == 0 && p.nblk >= 2 && a.norm_out == nullptr) {
+    const long t1 = ((tiles + sms - 1) / sms) * (long)p.nblk;
+    const long t2 = ((2 * tiles + sms - 1) / sms) * (long)((p.nblk + 1) / 2 + 6);
+    if (t2 < t1) split = 2;
+    const char* e = getenv("AGB_ATTN_SPLIT");
+    if (e && (e[0] == '1' || e[0] == '2')) split = e[0] - '0';
+  }
   void (*fn)(const AttnKParams) = nullptr;
   int slot = 0;
   switch (attn_poly_of8()) {
-    case 0: fn = attention_kernel<0>; slot = 0; break;
-    case 2: fn = attention_kernel<2>; slot = 1; break;
-    case 5: fn = attention_kernel<5>; slot = 3; break;
-    case 6: fn = attention_kernel<6>; slot = 4; break;
-    case 4: fn = attention_kernel<4>; slot = 2; break;
-    default: fn = attention_kernel<2>; slot = 1; break;
+    case 0: fn = split == 2 ? attention_kernel<0, 2> : attention_kernel<0, 1>; slot = 0; break;
+    case 4: fn = split == 2 ? attention_kernel<4, 2> : attention_kernel<4, 1>; slot = 2; break;
+    case 5: fn = split == 2 ? attention_kernel<5, 2> : attention_kernel<5, 1>; slot = 3; break;
+    case 6: fn = split == 2 ? attention_kernel<6, 2> : attention_kernel<6, 1>; slot = 4; break;
+    default: fn = split == 2 ? attention_kernel<2, 2> : attention_kernel<2, 1>; slot = 1; break;
   }
-  static thread_local unsigned char attr_done[64][5];
-  if (!attr_done[device][slot]) {
+  static thread_local unsigned char attr_done[64][2][5];
+  if (!attr_done[device][split - 1][slot]) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
     if (e != cudaSuccess) return set_error("ag_attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_done[device][slot] = 1;
+    attr_done[device][split - 1][slot] = 1;
   }
-  const long grid = (long)p.q_tiles * a.heads * a.batch;
-  if (grid > 2147483647L) return set_error("ag_attention_fwd: grid too large");
-  fn<<<(unsigned)grid, kAttThreads, kAttSmem, stream>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(tiles * split), 1, 1);
+  cfg.blockDim = dim3(kAttThreads, 1, 1);
+  cfg.dynamicSmemBytes = kAttSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)split;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
+  if (le != cudaSuccess) return set_error("ag_attention_fwd: launch failed: %s", cudaGetErrorString(le));
   return check_launch("ag_attention_fwd");
 }
 

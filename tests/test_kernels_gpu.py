@@ -52,6 +52,27 @@ def test_attention_softcap_bias(B, H, n):
     assert rel_err(out, want) < 1.2e-2
 
 
+def test_attention_key_split_matches_unsplit(monkeypatch):
+    """A sequence-parallel rank's shape (few query tiles, many keys) takes the 2-CTA key split (cluster + DSMEM
+    combine); it must agree with the same problem computed as part of a larger, unsplit launch."""
+    H, d, dv, n, nq = 8, 128, 192, 2048, 256
+    Q = g(1, n, H * d, seed=1).bfloat16().to(DEV)
+    K = g(1, 1, n, d, seed=2).bfloat16().to(DEV)
+    Vt = g(1, 1, dv, n, seed=3).bfloat16().to(DEV)
+    bias = g(1, H, n // 16, n // 16, seed=4).to(DEV)
+    O_full = torch.empty(1, n, H * dv, dtype=torch.bfloat16, device=DEV)
+    ops.attention(Q.view(1, n, H, d).permute(0, 2, 1, 3), K, Vt, O_full.view(1, n, H, dv).permute(0, 2, 1, 3), mode=0,
+                  scale=d ** -0.5, bias=bias, softcap=5.0)     # 128 tiles x 16 blocks: unsplit
+    Qs = Q[:, :nq].contiguous()
+    O_s = torch.empty(1, nq, H * dv, dtype=torch.bfloat16, device=DEV)
+    ops.attention(Qs.view(1, nq, H, d).permute(0, 2, 1, 3), K, Vt, O_s.view(1, nq, H, dv).permute(0, 2, 1, 3), mode=0,
+                  scale=d ** -0.5, bias=bias[:, :, : nq // 16].contiguous(), softcap=5.0)   # 16 tiles: split in two
+    torch.cuda.synchronize()
+    # the two halves are summed in fp32 before normalisation: differences are at most one bf16 ulp of the output
+    assert rel_err(O_s, O_full[:, :nq].float().cpu()) < 1e-2
+    assert (O_s.float() - O_full[:, :nq].float()).abs().max().item() <= 2 ** -7 * O_full.float().abs().max().item()
+
+
 @pytest.mark.parametrize("B,P", [(1, 4), (2, 24), (1, 136), (1, 1)])
 def test_attention_pair_rows(B, P):
     D = 128

