@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 # buffers defined by a formula in the reference (AG:541-543, AG:581): never randomised
-FORMULA_BUFFERS = ("rotary_emb.inv_freq", "rel_pos_features.dummy")
+FORMULA_BUFFERS = ("rotary_emb.inv_freq", "rel_pos_features.dummy", "rope.inv_freq")
 
 
 def _rng(seed: int, name: str) -> np.random.Generator:
@@ -41,6 +41,12 @@ def synth_tensor(seed: int, name: str, shape: Tuple[int, ...]) -> np.ndarray:
         return r.uniform(-0.1, 0.1, shape).astype(np.float32)
     if leaf == "weight" and ".embed." in "." + name:
         return r.standard_normal(shape).astype(np.float32)  # nn.Embedding default N(0, 1)
+    if leaf == "scale" and len(shape) == 1:      # TracksScaledPrediction.scale (AG:1386), used as softplus(scale)
+        return r.uniform(-0.5, 0.5, shape).astype(np.float32)
+    if leaf == "scale":                           # SpliceJunctionHead.scale [contexts, hidden] (AG:1333), init ones
+        return (1.0 + r.uniform(-0.2, 0.2, shape)).astype(np.float32)
+    if leaf == "offset":                          # SpliceJunctionHead.offset (AG:1334), init zeros
+        return r.uniform(-0.1, 0.1, shape).astype(np.float32)
     if leaf == "weight":
         fan_in = int(np.prod(shape[1:]))
         bound = 1.0 / math.sqrt(fan_in)

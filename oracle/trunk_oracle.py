@@ -293,3 +293,58 @@ def alphagenome_embeds(sd: SD, seq, organism_index, collect: Optional[Callable] 
     epair = output_pair_embedding(sd, "outembed_pair.", pair, organism_index)
     return dict(embeds_1bp=e1, embeds_128bp=e128, embeds_pair=epair, unet_output=unet_out, single_repr=single,
                 pairwise_repr=pair)
+
+
+# ---------------------------------------------------------------------------------------------- prediction heads
+# (`AlphaGenome.add_heads`, AG:1653-1682 — every organism's heads run on every sample, AG:1823-1850)
+def tracks_scaled_prediction(sd: SD, p: str, x):
+    """TracksScaledPrediction.forward AG:1378-1393: softplus(Linear(x)) * softplus(scale)."""
+    return F.softplus(linear(sd, p + "to_pred.", x)) * F.softplus(sd[p + "scale"])
+
+
+def contact_map_head(sd: SD, p: str, embeds_pair, organism_index):
+    """ContactMapHead.forward AG:1286-1299: symmetrize -> RMSNormWithBias -> + organism embedding -> GELU1702 -> Linear."""
+    x = 0.5 * (embeds_pair + embeds_pair.transpose(1, 2))
+    x = rms_norm_bias(sd, p + "norm.", x) + sd[p + "embed.weight"][organism_index][:, None, None, :]
+    return linear(sd, p + "proj.", gelu1702(x))
+
+
+def splice_rotary_table(hidden: int, n_contexts: int, max_positions: int = 2 ** 20):
+    """RotaryEmbedding(hidden, max_positions = 2**20)(n_contexts) AG:541-557: [contexts, hidden] angles."""
+    inv = rotary_inv_freq(hidden, max_positions)
+    ang = torch.arange(n_contexts, dtype=torch.float32)[:, None] * inv[None, :]
+    return ang.repeat_interleave(2, dim=-1)
+
+
+def splice_junction_head(sd: SD, p: str, embeds_1bp, donor_idx, acceptor_idx):
+    """SpliceJunctionHead.forward AG:1322-1376 -> softplus scores [B, donors, acceptors, contexts]."""
+    x_proj = linear(sd, p + "project.", embeds_1bp)                     # [B, L, hidden]
+    scale, offset = sd[p + "scale"], sd[p + "offset"]                   # [contexts, hidden]
+    ang = splice_rotary_table(scale.shape[1], scale.shape[0])           # the context index is the rotary position
+    b = torch.arange(x_proj.shape[0])[:, None]
+
+    def tissue_scaled_rope(idx):
+        x = x_proj[b, idx]                                              # [B, P, hidden]
+        x = x[:, :, None, :] * scale + offset                           # [B, P, contexts, hidden]
+        return apply_rope(ang, x)
+
+    d, a = tissue_scaled_rope(donor_idx), tissue_scaled_rope(acceptor_idx)
+    return F.softplus(torch.einsum("bdth,bath->bdat", d, a))
+
+
+@torch.no_grad()
+def alphagenome_heads(sd: SD, embeds: dict, organism_index, organisms, splice_donor_idx=None, splice_acceptor_idx=None):
+    """AlphaGenome.forward AG:1780-1852 after get_embeds, for heads registered with add_heads."""
+    out = {}
+    for org in organisms:
+        hp = f"heads.{org}."
+        o = dict()
+        o["1bp_tracks"] = tracks_scaled_prediction(sd, hp + "1bp_tracks.", embeds["embeds_1bp"])
+        o["128bp_tracks"] = tracks_scaled_prediction(sd, hp + "128bp_tracks.", embeds["embeds_128bp"])
+        o["contact_head"] = contact_map_head(sd, hp + "contact_head.", embeds["embeds_pair"], organism_index)
+        o["splice_logits"] = linear(sd, hp + "splice_logits.linear.", embeds["embeds_1bp"])                 # AG:1301-1310
+        o["splice_usage"] = torch.sigmoid(linear(sd, hp + "splice_usage.linear.", embeds["embeds_1bp"]))    # AG:1312-1321
+        if splice_donor_idx is not None:
+            o["splice_juncs"] = splice_junction_head(sd, hp + "splice_juncs.", embeds["embeds_1bp"], splice_donor_idx, splice_acceptor_idx)
+        out[org] = o
+    return out

@@ -46,3 +46,22 @@ def sample_rows(name: str, shape):
     stride = n // 64
     idx = np.unique(np.concatenate([np.arange(0, n, stride), np.arange(8), np.arange(n - 8, n)]))
     return torch.from_numpy(idx)
+
+
+# prediction heads: publication heads of both organisms on every sample (AG:1823-1850)
+HEAD_CASES = [
+    dict(name="heads_B2_L4096", B=2, L=4096, weight_seed=3, n_sites=12),
+    dict(name="heads_B1_L16384", B=1, L=16384, weight_seed=4, n_sites=40, first_org=1),   # 8x8 contact map, ragged site count
+]
+
+
+def make_head_inputs(case):
+    B, L = case["B"], case["L"]
+    rng = np.random.default_rng(99)
+    seq = rng.integers(0, 4, size=(B, L))
+    seq[0, 17] = -1
+    org = (np.arange(B, dtype=np.int64) + case.get("first_org", 0)) % 2
+    donor = np.sort(rng.choice(L, size=(B, case["n_sites"]), replace=True), axis=1)
+    acceptor = np.sort(rng.choice(L, size=(B, case["n_sites"]), replace=True), axis=1)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).astype(np.int64))
+    return t(seq), t(org), t(donor), t(acceptor)

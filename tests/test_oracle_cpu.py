@@ -61,3 +61,43 @@ def test_seed42_input_is_reference_fixture():
     seq, org = make_inputs(CASES[0])
     assert seq.shape == (1, 2048) and int(org[0]) == 0
     assert seq[0, :8].tolist() == np.random.default_rng(42).integers(0, 4, size=(1, 2048))[0, :8].tolist()
+
+
+# ----------------------------------------------------------------------------------------------- prediction heads
+from tests.golden_util import HEAD_CASES, make_head_inputs  # noqa: E402
+
+HEAD_NAMES = ["1bp_tracks", "128bp_tracks", "contact_head", "splice_logits", "splice_usage", "splice_juncs"]
+
+
+def head_shapes():
+    shapes = {}
+    for line in (GOLD / "state_dict_keys_heads.txt").read_text().splitlines():
+        m = re.match(r"(\S+) \((.*)\)", line)
+        shapes[m.group(1)] = tuple(int(x) for x in m.group(2).replace(",", " ").split())
+    return shapes
+
+
+def synth_sd_with_heads(seed):
+    sd = synth_sd(seed)
+    sd.update(synth_state_dict(head_shapes(), seed))
+    return sd
+
+
+@pytest.mark.parametrize("case", HEAD_CASES, ids=[c["name"] for c in HEAD_CASES])
+def test_oracle_heads_match_reference_golden(case):
+    """The publication heads of both organisms (add_heads(**publication_heads_config[...])) on every sample."""
+    g = np.load(GOLD / f"{case['name']}.npz")
+    seq, org, donor, acceptor = make_head_inputs(case)
+    assert np.array_equal(g["seq"].astype(np.int64), seq.numpy()) and np.array_equal(g["splice_donor_idx"], donor.numpy())
+    sd = synth_sd_with_heads(case["weight_seed"])
+    emb = O.alphagenome_embeds(sd, seq, org)
+    out = O.alphagenome_heads(sd, emb, org, ("human", "mouse"), donor, acceptor)
+    for organism in ("human", "mouse"):
+        for name in HEAD_NAMES:
+            got = out[organism][name]
+            if name in ("1bp_tracks", "splice_logits", "splice_usage"):
+                got = got[:, sample_rows("head", got.shape)]
+            want = g[f"{organism}/{name}"]
+            assert got.shape == want.shape, (organism, name, got.shape, want.shape)
+            err = np.abs(got.numpy() - want).max() / float(g[f"{organism}/{name}__absmax"])
+            assert err < 5e-5, (organism, name, err)
