@@ -106,7 +106,7 @@ class AgAttnArgs(C.Structure):
     ]
 
 
-ACT_NONE, ACT_GELU1702, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU1702, ACT_GELU_ERF, ACT_RELU, ACT_SOFTPLUS_MUL, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
 
 # every symbol include/agb200.h declares; tests check the built library exports all of them
 EXPORTED = [
@@ -127,6 +127,8 @@ EXPORTED = [
     "ag_rmsnorm_fwd",
     "ag_add_embed_norm_fwd",
     "ag_pair_out_embed_fwd",
+    "ag_rmsnorm_act_fwd",
+    "ag_splice_rope_fwd",
 ]
 
 _lib = None
@@ -167,6 +169,8 @@ def load() -> C.CDLL:
     lib.ag_rmsnorm_fwd.argtypes = [P] * 4 + [I64, I32, C.c_int, P]
     lib.ag_add_embed_norm_fwd.argtypes = [P] * 6 + [I32] * 3 + [C.c_int, P]
     lib.ag_pair_out_embed_fwd.argtypes = [P] * 6 + [I32] * 4 + [C.c_int, P]
+    lib.ag_rmsnorm_act_fwd.argtypes = [P] * 5 + [I64, I64, I32, I32, C.c_int, P]
+    lib.ag_splice_rope_fwd.argtypes = [P] * 6 + [I32] * 5 + [C.c_int, P]
     lib.ag_gemm_set_cta_group.argtypes = [C.c_int]
     lib.ag_gemm_set_cta_group.restype = C.c_int
     for name in EXPORTED[6:]:

@@ -211,4 +211,18 @@ int ag_pair_out_embed_fwd(const float* pair, const float* pairT, const float* w,
   return launch_pair_out_embed(pair, pairT, w, b, emb, out, B, rows, P, C, device, static_cast<cudaStream_t>(stream));
 }
 
+int ag_rmsnorm_act_fwd(const float* x, const float* w, const float* b, const float* add, void* out_bf16, int64_t rows,
+                       int64_t rows_per_batch, int32_t C, int32_t act, int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_rmsnorm_act(x, w, b, add, out_bf16, rows, rows_per_batch, C, act, device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_splice_rope_fwd(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
+                       void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t hidden, int32_t p_ld, int device,
+                       void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_splice_rope(x, scale, offset, cos_tab, sin_tab, out_bf16, B, P, T, hidden, p_ld, device,
+                            static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -289,7 +289,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ----------------------------------------------------------------------------------------
 // activations (reference: alphagenome.py:130-137 GELU1702; nn.GELU (erf) at :690, :810; ReLU :903)
 // ----------------------------------------------------------------------------------------
-enum ActMode : int { ACT_NONE = 0, ACT_GELU1702 = 1, ACT_GELU_ERF = 2, ACT_RELU = 3 };
+enum ActMode : int { ACT_NONE = 0, ACT_GELU1702 = 1, ACT_GELU_ERF = 2, ACT_RELU = 3, ACT_SOFTPLUS_MUL = 4, ACT_SIGMOID = 5 };
 
 __device__ __forceinline__ float act_apply(float x, int mode) {
   switch (mode) {

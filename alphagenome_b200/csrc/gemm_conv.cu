@@ -55,23 +55,31 @@ struct GemmKParams {
   unsigned int* err;
 };
 
-// Only ACT_NONE / ACT_GELU1702 occur in GEMM epilogues (checked on the host).
+// GEMM epilogue activations (checked on the host): ACT_NONE / ACT_GELU1702 for bf16 and fp32 outputs; fp32 outputs
+// also take the prediction heads' ACT_SOFTPLUS_MUL (softplus(v + shift) * scale, AG:1388-1393) and ACT_SIGMOID (AG:1321).
 __device__ __forceinline__ float gelu1702_fast(float x) {   // 0.5x + 0.5x*tanh(0.851x): one MUFU op
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx(0.851f * x), hx);
 }
 __device__ __forceinline__ float gelu1702_acc(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+// F.softplus (beta 1, threshold 20): max(x, 0) + log1p(exp(-|x|)); the log1p argument is at most 1
+__device__ __forceinline__ float softplus_acc(float x) {
+  const float t = __expf(-fabsf(x));
+  const float l = t < 1e-3f ? t * fmaf(-0.5f, t, 1.0f) : __logf(1.0f + t);
+  return fmaxf(x, 0.0f) + l;
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // One activated output for 4 consecutive channels of one row: dst = act(v*s + t), bf16 (fast GELU) or fp32.
-__device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool is_bf16, bool gelu, float4 v,
+__device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool is_bf16, int act, float4 v,
                                            const float4& s, const float4& t) {
   float4 y;
-  y.x = fmaf(v.x, s.x, t.x);
-  y.y = fmaf(v.y, s.y, t.y);
-  y.z = fmaf(v.z, s.z, t.z);
-  y.w = fmaf(v.w, s.w, t.w);
   if (is_bf16) {
-    if (gelu) {
+    y.x = fmaf(v.x, s.x, t.x);
+    y.y = fmaf(v.y, s.y, t.y);
+    y.z = fmaf(v.z, s.z, t.z);
+    y.w = fmaf(v.w, s.w, t.w);
+    if (act != ACT_NONE) {
       y.x = gelu1702_fast(y.x);
       y.y = gelu1702_fast(y.y);
       y.z = gelu1702_fast(y.z);
@@ -84,11 +92,27 @@ __device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool i
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(base + (size_t)elem_off * 2) = pk;
   } else {
-    if (gelu) {
-      y.x = gelu1702_acc(y.x);
-      y.y = gelu1702_acc(y.y);
-      y.z = gelu1702_acc(y.z);
-      y.w = gelu1702_acc(y.w);
+    if (act == ACT_SOFTPLUS_MUL) {
+      y.x = softplus_acc(v.x + t.x) * s.x;
+      y.y = softplus_acc(v.y + t.y) * s.y;
+      y.z = softplus_acc(v.z + t.z) * s.z;
+      y.w = softplus_acc(v.w + t.w) * s.w;
+    } else {
+      y.x = fmaf(v.x, s.x, t.x);
+      y.y = fmaf(v.y, s.y, t.y);
+      y.z = fmaf(v.z, s.z, t.z);
+      y.w = fmaf(v.w, s.w, t.w);
+      if (act == ACT_GELU1702) {
+        y.x = gelu1702_acc(y.x);
+        y.y = gelu1702_acc(y.y);
+        y.z = gelu1702_acc(y.z);
+        y.w = gelu1702_acc(y.w);
+      } else if (act == ACT_SIGMOID) {
+        y.x = sigmoid_acc(y.x);
+        y.y = sigmoid_acc(y.y);
+        y.z = sigmoid_acc(y.z);
+        y.w = sigmoid_acc(y.w);
+      }
     }
     *reinterpret_cast<float4*>(base + (size_t)elem_off * 4) = y;
   }
@@ -239,9 +263,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     uint32_t aphase = 0;
     const float post = g.post_scale ? __ldg(g.post_scale) : 1.0f;
     const bool relu = g.relu != 0;
-    const bool a16 = g.actA.dtype == 0, aG = g.actA.act != ACT_NONE;
-    const bool b16 = g.actB.dtype == 0, bG = g.actB.act != ACT_NONE;
-    const bool p16 = g.actP.dtype == 0, pG = g.actP.act != ACT_NONE;
+    const bool a16 = g.actA.dtype == 0, b16 = g.actB.dtype == 0, p16 = g.actP.dtype == 0;
+    const int aG = g.actA.act, bG = g.actB.act, pG = g.actP.act;
     const bool has_poolf = kPool && g.pool != nullptr, has_actP = kPool && g.actP.ptr != nullptr;
     const int nchunks = p.n_tile / kEpiCols;
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
@@ -429,7 +452,9 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
         (reinterpret_cast<uintptr_t>(o->scale) & 15) || (reinterpret_cast<uintptr_t>(o->shift) & 15))
       return set_error("ag_gemm_fwd: activated outputs need ld/bstride multiples of 4 and aligned pointers");
     if (o->dtype != 0 && o->dtype != 1) return set_error("ag_gemm_fwd: bad output dtype %d", o->dtype);
-    if (o->act != AG_ACT_NONE && o->act != AG_ACT_GELU1702) return set_error("ag_gemm_fwd: epilogue activations are AG_ACT_NONE or AG_ACT_GELU1702 (got %d)", o->act);
+    const bool head_act = o->act == AG_ACT_SOFTPLUS_MUL || o->act == AG_ACT_SIGMOID;
+    if (o->act != AG_ACT_NONE && o->act != AG_ACT_GELU1702 && !(head_act && o->dtype == 1))
+      return set_error("ag_gemm_fwd: epilogue activations are AG_ACT_NONE / AG_ACT_GELU1702, or AG_ACT_SOFTPLUS_MUL / AG_ACT_SIGMOID on fp32 outputs (got act %d, dtype %d)", o->act, o->dtype);
   }
   if ((reinterpret_cast<uintptr_t>(a.pre_scale) | reinterpret_cast<uintptr_t>(a.pre_shift)) & 15)
     return set_error("ag_gemm_fwd: pre_scale/pre_shift must be 16-byte aligned");

@@ -14,7 +14,7 @@ calling a forward without a B200 and the built library raises.
 """
 from __future__ import annotations
 
-from collections import namedtuple
+from collections import defaultdict, namedtuple
 
 import torch
 from torch import nn
@@ -322,7 +322,42 @@ class AlphaGenome(nn.Module):
         self.dim_128bp = 2 * last_dim
         self.dim_contacts = self.transformer_unet.transformer.dim_pairwise
         self.heads = nn.ModuleDict()
+        self.head_forward_arg_names = defaultdict(dict)
+        self.head_forward_arg_maps = defaultdict(dict)
         self.cuda_graphs = False  # see enable_cuda_graphs()
+
+    # ---- prediction heads: same registration API as the reference (AG:1621-1682) ----
+    def add_head(self, organism, head_name, head: nn.Module, head_input_kwarg_names=None):
+        """AG:1621-1651."""
+        from .heads import get_function_arg_names
+
+        if isinstance(head_input_kwarg_names, str):
+            head_input_kwarg_names = (head_input_kwarg_names,)
+        if organism not in self.heads:
+            self.heads[organism] = nn.ModuleDict()
+        self.heads[organism][head_name] = head
+        head_forward_arg_names = get_function_arg_names(head.forward)
+        self.head_forward_arg_names[organism][head_name] = head_forward_arg_names if head_input_kwarg_names is None else head_input_kwarg_names
+        arg_map = dict()
+        if head_input_kwarg_names is not None:
+            arg_map = dict(zip(head_input_kwarg_names, head_forward_arg_names))
+        self.head_forward_arg_maps[organism][head_name] = arg_map
+
+    def add_heads(self, organism, num_tracks_1bp, num_tracks_128bp, num_tracks_contacts, num_splicing_contexts,
+                  hidden_dim_splice_juncs=512):
+        """AG:1653-1682: the publication heads of one organism (`add_heads(**publication_heads_config['human'])`)."""
+        from .heads import ContactMapHead, SpliceJunctionHead, SpliceSiteClassifier, SpliceSiteUsage, TracksScaledPrediction
+
+        organism_heads = (
+            ("1bp_tracks", TracksScaledPrediction(self.dim_1bp, num_tracks_1bp), ("embeds_1bp",)),
+            ("128bp_tracks", TracksScaledPrediction(self.dim_128bp, num_tracks_128bp), ("embeds_128bp",)),
+            ("contact_head", ContactMapHead(self.dim_contacts, num_tracks_contacts, self.num_organisms)),
+            ("splice_logits", SpliceSiteClassifier(self.dim_1bp)),
+            ("splice_usage", SpliceSiteUsage(self.dim_1bp, num_splicing_contexts)),
+            ("splice_juncs", SpliceJunctionHead(self.dim_1bp, hidden_dim_splice_juncs, num_splicing_contexts)),
+        )
+        for args in organism_heads:
+            self.add_head(organism, *args)
 
     def enable_cuda_graphs(self, enabled: bool = True):
         """Replay the forward from a CUDA graph (per input shape).  Outputs are then static buffers that the next
@@ -352,8 +387,19 @@ class AlphaGenome(nn.Module):
             return embeds
         return embeds, TransformerUnetOutput(out["unet_output"], out["single_repr"], out["pairwise_repr"])
 
+    @torch.no_grad()
     def forward(self, seq, organism_index, return_embeds=False, **head_kwargs):
-        """AG:1780-1852 with no heads registered (heads are SURVEY 8f 'next'): returns Embeds."""
-        if len(self.heads) != 0 and not return_embeds:
-            raise NotImplementedError("prediction heads are outside the B200 hot path in this round (SURVEY.md 8f #2)")
-        return self.get_embeds(seq, organism_index)
+        """AG:1780-1852: Embeds when no heads are registered (or return_embeds), else {organism: {head: prediction}}
+        with every organism's heads run on every sample."""
+        if len(self.heads) == 0 or return_embeds:
+            return self.get_embeds(seq, organism_index)
+        from .heads import HeadsEngine
+        from .trunk import engine_for
+
+        organism_index = self._organism_tensor(seq, organism_index).to(seq.device).long()
+        eng = engine_for(self.transformer_unet, self)
+        out = eng.run_embeds(seq, organism_index, want_head_operands=True)
+        if getattr(self, "_heads_engine", None) is None:
+            object.__setattr__(self, "_heads_engine", HeadsEngine(self))
+        plan = eng.sp.plan(seq.shape[1]) if eng.sp is not None else None
+        return self._heads_engine.run(out, organism_index, head_kwargs, sp=eng.sp, plan=plan)

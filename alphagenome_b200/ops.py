@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU1702, ACT_GELU_ERF, ACT_NONE, ACT_RELU, AgAttnArgs, AgEpiOut, AgGemmArgs  # noqa: F401
+from ._lib import ACT_GELU1702, ACT_GELU_ERF, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS_MUL, AgAttnArgs, AgEpiOut, AgGemmArgs  # noqa: F401
 
 
 # bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per ag_gemm_fwd launch
@@ -355,3 +355,28 @@ def pair_out_embed(pair, w, b, emb, out, pairT=None) -> None:
         _f32(t, nm)
     _require(pairT.numel() == pair.numel(), "pairT size mismatch")
     _lib.check(_lib.load().ag_pair_out_embed_fwd(pair.data_ptr(), pairT.data_ptr(), w.data_ptr(), b.data_ptr(), emb.data_ptr(), out.data_ptr(), B, rows, P, Cc, _dev(pair), _stream()))
+
+
+def rmsnorm_act(x, w, b, out, add=None, rows_per_batch: Optional[int] = None, act: int = ACT_NONE) -> None:
+    """ag_rmsnorm_act_fwd: out = act(RMSNormWithBias(x) + add[batch]) in bf16; x [..., C] fp32, add [batches, C] or None."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    for t, nm in ((x, "x"), (w, "w"), (b, "b"), (add, "add")):
+        _f32(t, nm)
+    _require(out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() == x.numel(), "out must be contiguous bf16 of x's size")
+    if add is not None:
+        _require(rows_per_batch is not None and add.shape[-1] == Cc and add.numel() // Cc * rows_per_batch == rows, "add must be [rows / rows_per_batch, C]")
+    _lib.check(_lib.load().ag_rmsnorm_act_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), _ptr(add), out.data_ptr(), rows,
+                                              rows_per_batch or rows, Cc, int(act), _dev(x), _stream()))
+
+
+def splice_rope(x, scale, offset, cos_tab, sin_tab, out) -> None:
+    """ag_splice_rope_fwd: x fp32 [B, P, H]; scale/offset [T, H]; cos/sin [T, H/2]; out bf16 [B, T, >=P, H]."""
+    B, P, Hd = x.shape
+    T = scale.shape[0]
+    for t, nm in ((x, "x"), (scale, "scale"), (offset, "offset"), (cos_tab, "cos"), (sin_tab, "sin")):
+        _f32(t, nm)
+    _require(tuple(scale.shape) == (T, Hd) and tuple(offset.shape) == (T, Hd) and tuple(cos_tab.shape) == (T, Hd // 2) and tuple(sin_tab.shape) == (T, Hd // 2), "scale/offset [T, H], cos/sin [T, H/2]")
+    _require(out.dtype == torch.bfloat16 and out.is_contiguous() and out.dim() == 4 and out.shape[0] == B and out.shape[1] == T and out.shape[2] >= P and out.shape[3] == Hd, "out must be bf16 [B, T, >=P, H]")
+    _lib.check(_lib.load().ag_splice_rope_fwd(x.data_ptr(), scale.data_ptr(), offset.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), out.data_ptr(),
+                                              B, P, T, Hd, out.shape[2], _dev(x), _stream()))

@@ -169,6 +169,18 @@ class SeqParallel:
             off += w
         return res
 
+    def all_reduce_sum(self, x: torch.Tensor) -> torch.Tensor:
+        """Sum over ranks (splice-junction head: each gathered site row is non-zero on exactly one rank)."""
+        x = x.contiguous()
+        if self._stage and x.is_cuda:
+            h = x.cpu()
+            dist.all_reduce(h, group=self.group)
+            x = h.to(x.device)
+        else:
+            dist.all_reduce(x, group=self.group)
+        self.n_collectives += 1
+        return x
+
     def transpose_blocks(self, pair: torch.Tensor) -> torch.Tensor:
         """pair: this rank's rows [B, P_loc, P, C] -> pairT [world, B, P_loc, P_loc, C] with
         pairT[s, b, jl, il] = pair_global[b, s*P_loc + jl, row_off + il]  (the layout ag_pair_out_embed_fwd reads)."""

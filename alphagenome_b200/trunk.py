@@ -410,7 +410,7 @@ class TrunkEngine:
 
     # ------------------------------------------------------------------------------------------ public
     @torch.no_grad()
-    def run(self, seq, org_embed, organism_index=None, with_embeds=False):
+    def run(self, seq, org_embed, organism_index=None, with_embeds=False, want_head_operands=False):
         """seq: int64 [B, L] — the WHOLE context on every rank.  With `self.sp` set (sequence parallel) each rank
         computes and returns only its shard: bp [r L/G, (r+1) L/G), the matching tokens, and its pair rows."""
         if not seq.is_cuda:
@@ -461,11 +461,16 @@ class TrunkEngine:
             assert (n << shift) == Lfull
             t1 = o1["table"].index_select(0, organism_index)
             e1 = torch.empty(B, Lfull, o1["W"].shape[1], **f32)
-            ops.gemm(unet_b16, o1["W"], pre_shift=o1["b"], res=skp, res_shift=shift, actA=Act(e1, o1["s"], t1, ACT_GELU1702))
+            # prediction heads take embeds_1bp as a bf16 MMA operand: emitted by the same epilogue when asked for
+            e1_b16 = torch.empty(B, Lfull, o1["W"].shape[1], **bf) if want_head_operands else None
+            ops.gemm(unet_b16, o1["W"], pre_shift=o1["b"], res=skp, res_shift=shift, actA=Act(e1, o1["s"], t1, ACT_GELU1702),
+                     actB=Act(e1_b16, o1["s"], t1, ACT_GELU1702) if want_head_operands else None)
             epair = torch.empty_like(pair)
             pairT = self.sp.transpose_blocks(pair) if sharded else None  # symmetrize needs pair[j, i] (AG:1253)
             ops.pair_out_embed(pair, op["w"], op["b"], op["emb"].index_select(0, organism_index).contiguous(), epair, pairT=pairT)
-            out.update(embeds_1bp=e1, embeds_128bp=e128, embeds_pair=epair)
+            out.update(embeds_1bp=e1, embeds_128bp=e128, embeds_pair=epair, embeds_128bp_b16=e128_b16)
+            if want_head_operands:
+                out.update(embeds_1bp_b16=e1_b16)
         return out
 
     def run_embeds_graphed(self, seq, organism_index):
@@ -500,10 +505,10 @@ class TrunkEngine:
     def run_trunk(self, seq, pre_attend_embed=None):
         return self.run(seq, pre_attend_embed, with_embeds=False)
 
-    def run_embeds(self, seq, organism_index):
+    def run_embeds(self, seq, organism_index, want_head_operands=False):
         P = self.pack(seq.device)
         if "org" not in P:
             raise ops._lib.AgbError("run_embeds needs the AlphaGenome shell (organism / output embeddings)")
         organism_index = organism_index.to(seq.device).long()
         org = P["org"].index_select(0, organism_index)
-        return self.run(seq, org, organism_index=organism_index, with_embeds=True)
+        return self.run(seq, org, organism_index=organism_index, with_embeds=True, want_head_operands=want_head_operands)

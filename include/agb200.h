@@ -36,7 +36,10 @@ enum AgAct {
   AG_ACT_NONE = 0,
   AG_ACT_GELU1702 = 1, /* x * sigmoid(1.702 x)            AG:130-137 */
   AG_ACT_GELU_ERF = 2, /* nn.GELU() (exact erf)           AG:690, AG:810 */
-  AG_ACT_RELU = 3      /* nn.ReLU()                       AG:903 */
+  AG_ACT_RELU = 3,     /* nn.ReLU()                       AG:903 */
+  /* prediction heads (ag_gemm_fwd fp32 outputs only): */
+  AG_ACT_SOFTPLUS_MUL = 4, /* softplus(v + shift[c]) * scale[c]   TracksScaledPrediction AG:1388-1393 (scale = softplus(param)) */
+  AG_ACT_SIGMOID = 5       /* sigmoid(v * scale[c] + shift[c])    SpliceSiteUsage AG:1321 */
 };
 
 /* One "activated" epilogue output:  dst[b, row, c] = act( v * scale[c] + shift[b?, c] )
@@ -64,7 +67,8 @@ typedef struct AgEpiOut {
  *   v = acc * pre_scale[n] + pre_shift[n];  if relu: v = max(v, 0)
  *   if res && n < res_ch: v += res[b, r >> res_shift, n]
  *   if post_scale: v *= *post_scale
- *   out[b, r, n] = v;  actA / actB[b, r, n] = act(v * scale + shift)        (act: AG_ACT_NONE or AG_ACT_GELU1702)
+ *   out[b, r, n] = v;  actA / actB[b, r, n] = act(v * scale + shift)        (act: AG_ACT_NONE or AG_ACT_GELU1702;
+ *                                                                           fp32 outputs also AG_ACT_SOFTPLUS_MUL, AG_ACT_SIGMOID)
  *   pool[b, r/2, n] = max(v[r], v[r^1]);  actP[b, r/2, n] = act(pool * scale + shift)      (maxpool2, AG:468)
  *
  * A rows outside [0, a_rows) read as zero (the conv's zero padding, AG:448); rows are addressed as
@@ -206,6 +210,20 @@ int ag_add_embed_norm_fwd(const float* x, const float* emb, const float* scale, 
  * pairT[s][b][jl][il] = pair_global[b][s*rows + jl][i_off + il] (one rank: rows == P and pairT == pair). */
 int ag_pair_out_embed_fwd(const float* pair, const float* pairT, const float* w, const float* b, const float* emb,
                           float* out, int32_t B, int32_t rows, int32_t P, int32_t C, int device, void* stream);
+
+/* --- prediction heads; their contractions run on ag_gemm_fwd ---------------------------- */
+
+/* ContactMapHead AG:1292-1298 after symmetrize (embeds_pair is already symmetric): RMSNormWithBias over the last dim,
+ * + add[row / rows_per_batch][:] (the organism embedding; NULL = none), activation -> bf16 [rows][C] */
+int ag_rmsnorm_act_fwd(const float* x, const float* w, const float* b, const float* add, void* out_bf16, int64_t rows,
+                       int64_t rows_per_batch, int32_t C, int32_t act, int device, void* stream);
+
+/* SpliceJunctionHead.tissue_scaled_rope AG:1338-1361: x fp32 [B][P][hidden] (projected splice-site rows),
+ * scale/offset fp32 [T][hidden], cos/sin fp32 [T][hidden/2] (rotary position = context index) ->
+ * bf16 [B][T][p_ld][hidden] with out[b][t][p] = rope_t(x[b][p] * scale[t] + offset[t]) (rows p >= P untouched) */
+int ag_splice_rope_fwd(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
+                       void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t hidden, int32_t p_ld, int device,
+                       void* stream);
 
 /* library / error plumbing */
 int ag_version(void);

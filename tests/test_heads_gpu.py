@@ -1,0 +1,87 @@
+"""-m gpu: the publication prediction heads of both organisms on the B200 path against golden outputs
+of the unmodified reference (tests/golden/heads_*.npz, tools/make_golden_heads.py).
+north_star tolerance for head outputs: Pearson >= 0.999; max|d| / max|ref| is reported and bounded at 3e-2
+(a head stacks one more bf16 contraction on embeddings that are themselves within 1e-2)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from alphagenome_b200.init_weights import apply_synth_weights
+from alphagenome_b200.model import AlphaGenome, publication_heads_config
+from tests.golden_util import HEAD_CASES, make_head_inputs, sample_rows
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+HEAD_NAMES = ["1bp_tracks", "128bp_tracks", "contact_head", "splice_logits", "splice_usage", "splice_juncs"]
+
+_M = {}
+
+
+def model_with_heads(seed):
+    if "m" not in _M:
+        m = AlphaGenome()
+        for org in ("human", "mouse"):
+            m.add_heads(**publication_heads_config[org])
+        _M["m"] = m.cuda().eval()
+    apply_synth_weights(_M["m"], seed=seed)
+    return _M["m"]
+
+
+def pearson(a, b):
+    a = a.astype(np.float64).ravel() - a.mean()
+    b = b.astype(np.float64).ravel() - b.mean()
+    return float((a * b).sum() / np.sqrt((a * a).sum() * (b * b).sum()))
+
+
+@pytest.mark.parametrize("case", HEAD_CASES, ids=[c["name"] for c in HEAD_CASES])
+def test_heads_match_reference_golden(case):
+    g = np.load(GOLD / f"{case['name']}.npz")
+    seq, org, donor, acceptor = make_head_inputs(case)
+    model = model_with_heads(case["weight_seed"])
+    out = model(seq.cuda(), org.cuda(), splice_donor_idx=donor.cuda(), splice_acceptor_idx=acceptor.cuda())
+    torch.cuda.synchronize()
+    assert set(out) == {"human", "mouse"}
+    report = {}
+    for organism in ("human", "mouse"):
+        assert list(out[organism]) == HEAD_NAMES
+        for name in HEAD_NAMES:
+            got = out[organism][name].float().cpu()
+            if name in ("1bp_tracks", "splice_logits", "splice_usage"):
+                got = got[:, sample_rows("head", got.shape)]
+            want = g[f"{organism}/{name}"]
+            assert tuple(got.shape) == want.shape, (organism, name, tuple(got.shape), want.shape)
+            err = np.abs(got.numpy() - want).max() / float(g[f"{organism}/{name}__absmax"])
+            r = pearson(got.numpy(), want)
+            report[f"{organism}/{name}"] = (round(err, 5), round(r, 6))
+            assert r >= 0.999, (organism, name, r, err)
+            assert err <= 3e-2, (organism, name, err)
+    print(report)
+
+
+def test_forward_without_head_kwargs_matches_reference_behaviour():
+    """splice_juncs needs splice_donor_idx / splice_acceptor_idx: like the reference (AG:1838), a missing head input is
+    a KeyError; return_embeds still short-circuits the heads (AG:1802)."""
+    model = model_with_heads(0)
+    seq = torch.randint(0, 4, (1, 2048), device="cuda")
+    emb = model(seq, 0, return_embeds=True)
+    assert tuple(emb.embeds_1bp.shape) == (1, 2048, 1536)
+    with pytest.raises(KeyError):
+        model(seq, 0)
+
+
+def test_custom_head_is_called_like_the_reference():
+    """add_head with a user module and explicit input names (AG:1621-1651): the module is simply called on the embeddings."""
+
+    class MeanHead(torch.nn.Module):
+        def forward(self, x):
+            return x.mean(dim=1)
+
+    m = AlphaGenome().cuda().eval()
+    apply_synth_weights(m, seed=0)
+    m.add_head("human", "mean128", MeanHead(), "embeds_128bp")
+    seq = torch.randint(0, 4, (1, 2048), device="cuda")
+    out = m(seq, 0)
+    emb = m(seq, 0, return_embeds=True)
+    assert torch.allclose(out["human"]["mean128"], emb.embeds_128bp.mean(dim=1))

@@ -125,3 +125,23 @@ def test_install_on_the_real_reference_model_packs_identically():
     # and the reference's own RelativePosFeatures.forward agrees with ours (AG:587-604)
     want = ref.transformer_unet.transformer.rel_pos_features(torch.zeros(1, 8 * 16, 4))
     assert torch.equal(feats, want)
+
+
+def test_heads_state_dict_matches_reference():
+    """add_heads(**publication_heads_config[org]) registers the reference's head parameters under the reference's names
+    and shapes (tests/golden/state_dict_keys_heads.txt is dumped from the reference, tools/make_golden_heads.py)."""
+    from alphagenome_b200.model import AlphaGenome, publication_heads_config
+
+    m = AlphaGenome()
+    for org in ("human", "mouse"):
+        m.add_heads(**publication_heads_config[org])
+    sd = m.state_dict()
+    want = {}
+    for line in (Path(__file__).resolve().parent / "golden" / "state_dict_keys_heads.txt").read_text().splitlines():
+        k, shape = line.split(" ", 1)
+        want[k] = shape
+    got = {k: str(tuple(v.shape)) for k, v in sd.items() if k.startswith("heads.")}
+    assert got == want
+    assert m.head_forward_arg_names["human"]["splice_juncs"] == ["embeds_1bp", "splice_donor_idx", "splice_acceptor_idx"]
+    assert tuple(m.head_forward_arg_names["mouse"]["1bp_tracks"]) == ("embeds_1bp",)
+    assert m.head_forward_arg_maps["human"]["1bp_tracks"] == {"embeds_1bp": "x"}
