@@ -126,12 +126,13 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(L, gpus):
+def workload_config(L, gpus, heads=False):
     par = ("single GPU" if gpus == 1 else
            f"sp{gpus}: ONE {L} bp context sharded along the sequence over {gpus} GPUs (2048 bp recomputed conv halos, "
            f"K/V + pooled-row all-gathers and one pair all-to-all over NCCL/NVLink)")
     return dict(workload="AlphaGenome() trunk forward (conv encoder + 9-layer tower with pair blocks + conv decoder + output "
-                         f"embeddings), B=1 x {L} bp, synthetic weights (default 7-stage dims 768..1536), no heads",
+                         f"embeddings), B=1 x {L} bp, synthetic weights (default 7-stage dims 768..1536), "
+                         + ("+ publication heads of human and mouse (add_heads(**publication_heads_config[...]), 64 splice sites)" if heads else "no heads"),
                 length_bp=L, global_batch=1, parallelism=par,
                 l2="per-step inputs+activations >> 126 MB L2 (1bp activations are GBs); no explicit flush needed")
 
@@ -146,6 +147,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--heads", action="store_true",
+                    help="secondary workload (BASELINE config 3/4): trunk + the publication heads of human and mouse; the default "
+                         "(headline) workload is the trunk forward alone, as BASELINE.json's metric says")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -172,7 +176,13 @@ def main():
     _lib.check(_lib.load().ag_check_device(local_rank))
     from alphagenome_b200.trunk import engine_for
 
-    model = AlphaGenome().to(dev).eval()
+    model = AlphaGenome()
+    if args.heads:
+        from alphagenome_b200.model import publication_heads_config
+
+        for organism in ("human", "mouse"):
+            model.add_heads(**publication_heads_config[organism])
+    model = model.to(dev).eval()
     apply_synth_weights(model, seed=0)
     eng = engine_for(model.transformer_unet, model)
     if world > 1:
@@ -193,8 +203,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    head_kw = {}
+    if args.heads:
+        rs = np.random.default_rng(7)
+        head_kw = dict(splice_donor_idx=torch.from_numpy(np.sort(rs.choice(L, size=(B, 64)), axis=1)).to(dev),
+                       splice_acceptor_idx=torch.from_numpy(np.sort(rs.choice(L, size=(B, 64)), axis=1)).to(dev))
+
     def step_resident():
-        return model(tok_dev, org_dev)
+        return model(tok_dev, org_dev, **head_kw)
 
     from alphagenome_b200.pipeline import HostPipeline
 
@@ -203,9 +219,29 @@ def main():
     # reference's get_embeds -> heads flow); HostPipeline double-buffers the read-back behind the next forward
     pipe = HostPipeline(model)
 
+    heads_host = {}
+
     def run_e2e(k):
         pipe.h2d_bytes = pipe.d2h_bytes = 0
-        return pipe.run((tok_host, org_host) for _ in range(k))
+        if not args.heads:
+            return pipe.run((tok_host, org_host) for _ in range(k))
+        # heads workload: sequential H2D -> forward + heads -> D2H of the 128 bp tracks, contact maps and splice junctions of
+        # both organisms (the 1 bp tracks, 16 GB at 1 Mbp, stay on the device)
+        for _ in range(k):
+            t = tok_host.to(dev, non_blocking=True)
+            o = org_host.to(dev, non_blocking=True)
+            pipe.h2d_bytes += tok_host.numel() * 8 + org_host.numel() * 8
+            res = model(t, o, **head_kw)
+            for organism, heads in res.items():
+                for name in ("128bp_tracks", "contact_head", "splice_juncs"):
+                    src = heads[name]
+                    key = (organism, name)
+                    if key not in heads_host:
+                        heads_host[key] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                    heads_host[key].copy_(src, non_blocking=True)
+                    pipe.d2h_bytes += src.numel() * src.element_size()
+            torch.cuda.current_stream().synchronize()
+        return k
 
     for _ in range(args.warmup):
         step_resident()
@@ -276,11 +312,13 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None,
                 dtype="bf16 operands / fp32 accumulate + fp32 residual stream",
-                data="synthetic", config=workload_config(L, world),
+                data="synthetic", config=workload_config(L, world, args.heads),
                 e2e=dict(value=e2e, unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         how="alphagenome_b200.pipeline.HostPipeline: per step H2D of the pinned host tokens, forward, D2H of "
-                             "embeds_128bp + embeds_pair into pinned host buffers; the read-back is double-buffered behind the next forward"),
-                gpu_launches=int(launches), launch_mode="cuda-graph replay" if not args.no_graph else "eager",
+                         how=("sequential per step: H2D of the pinned host tokens, forward + heads, D2H of the 128 bp tracks, contact maps "
+                              "and splice junctions of both organisms into pinned host buffers" if args.heads else
+                              "alphagenome_b200.pipeline.HostPipeline: per step H2D of the pinned host tokens, forward, D2H of "
+                              "embeds_128bp + embeds_pair into pinned host buffers; the read-back is double-buffered behind the next forward")),
+                gpu_launches=int(launches), launch_mode="cuda-graph replay" if not (args.no_graph or args.heads) else "eager",
                 clocks=clocks,
                 roofline=dict(kernel="gemm_conv_kernel (tcgen05 implicit-GEMM conv/linear), rank 0", bound="tensor", achieved=achieved,
                               peak=pk["tf_sustained"], unit="TFLOP/s", frac=(achieved / pk["tf_sustained"]) if achieved else None,

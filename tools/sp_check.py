@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--length", type=int, default=32768)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--same-gpu", action="store_true")
+    ap.add_argument("--heads", action="store_true", help="also run the publication heads of both organisms sharded vs unsharded")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", 0 if args.same_gpu else local)
@@ -54,6 +55,35 @@ def main():
             gathered[k] = eng.sp.gather_rows(v.view(Bq, Pl, Pn * C)).view(Bq, world * Pl, Pn, C)
         else:
             gathered[k] = eng.sp.gather_rows(v)
+    head_rep = None
+    if args.heads:
+        from alphagenome_b200.model import publication_heads_config
+
+        for o in ("human", "mouse"):
+            model.add_heads(**publication_heads_config[o])
+        model.cuda()
+        apply_synth_weights(model, seed=4)
+        rng = np.random.default_rng(3)
+        donor = torch.from_numpy(np.sort(rng.choice(L, size=(B, 24)), axis=1)).to(dev)
+        acceptor = torch.from_numpy(np.sort(rng.choice(L, size=(B, 24)), axis=1)).to(dev)
+        sharded = model(seq, org, splice_donor_idx=donor, splice_acceptor_idx=acceptor)
+        torch.cuda.synchronize()
+        hg = {}
+        for o, heads in sharded.items():
+            for name, v in heads.items():
+                v = v.contiguous()
+                if name == "splice_juncs":
+                    hg[(o, name)] = v                                   # replicated on every rank
+                elif v.dim() == 4:
+                    Bq, Pl, Pn, C = v.shape
+                    hg[(o, name)] = eng.sp.gather_rows(v.view(Bq, Pl, Pn * C)).view(Bq, world * Pl, Pn, C)
+                else:
+                    hg[(o, name)] = eng.sp.gather_rows(v)
+        eng.sp = None
+        if rank == 0:
+            full = model(seq, org, splice_donor_idx=donor, splice_acceptor_idx=acceptor)
+            torch.cuda.synchronize()
+            head_rep = {f"{o}/{n}": ((hg[(o, n)] - full[o][n]).abs().max() / full[o][n].abs().max()).item() for (o, n) in hg}
     eng.sp = None
     if rank == 0:
         emb, tu = model.get_embeds(seq, org, return_unet_transformer_outputs=True)
@@ -64,6 +94,9 @@ def main():
         # shards are bit-identical to the unsharded forward except where a rank's attention takes the 2-CTA key split
         # (few query tiles): its fp32 partial sums are added in a different order, i.e. one bf16 ulp in a few outputs
         ok = all(v <= 5e-3 for v in rep.values())
+        if head_rep is not None:
+            ok = ok and all(v <= 5e-3 for v in head_rep.values())
+            print("SP_HEADS " + json.dumps(head_rep), flush=True)
         print("SP_CHECK " + json.dumps(dict(ok=ok, bitwise=all(v == 0.0 for v in rep.values()), world=world, L=L, B=B, collectives=ncoll, max_rel_diff=rep)), flush=True)
     # leave without a collective teardown: a barrier/destroy after rank 0's extra (unsharded) forward once hung the
     # 2-GPU check until its timeout; every result is already printed
