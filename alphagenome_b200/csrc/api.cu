@@ -4,6 +4,7 @@
 #include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -17,6 +18,15 @@ static unsigned int* g_err_host[64] = {nullptr};
 static unsigned int* g_err_dev[64] = {nullptr};
 static int g_sm_count[64] = {0};
 static int g_cc[64] = {0};
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 int set_error(const char* fmt, ...) {
   va_list ap;

@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // set-up above overlaps the previous kernel's tail; global memory is only read from here on
   const uint32_t tmem_S = tmem_base;              // 2 x 128 columns (P aliases the S stage it was computed from)
   const uint32_t tmem_O = tmem_base + kTmemO;     // dv columns
   const uint32_t tmem_Q = tmem_base + kTmemQ;     // 64 columns: 128 bf16 per row
@@ -574,13 +576,15 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
   cfg.blockDim = dim3(kAttThreads, 1, 1);
   cfg.dynamicSmemBytes = kAttSmem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)split;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
   if (le != cudaSuccess) return set_error("ag_attention_fwd: launch failed: %s", cudaGetErrorString(le));
   return check_launch("ag_attention_fwd");

@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may be scheduled as our CTAs retire ...
+  pdl_wait();                // ... and we read nothing from global memory before the previous kernel has completed
 
   const int iters = g.taps * p.kblocks;
   const uint32_t b_bytes = (uint32_t)(p.n_tile / CG) * kBlockK * 2;   // this CTA's share of the W tile
@@ -507,13 +509,15 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cg;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
   if (le != cudaSuccess) return set_error("ag_gemm_fwd: launch failed: %s", cudaGetErrorString(le));
   return check_launch("ag_gemm_fwd");

@@ -22,6 +22,8 @@ int sm_count(int device);
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box);
 
+// programmatic dependent launch of the GEMM / attention kernels (env AGB_PDL=0 disables)
+bool pdl_enabled();
 extern std::atomic<int> g_gemm_cta_group;   // 0 auto, 1, 2 (ag_gemm_set_cta_group)
 int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream);
 int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream);

@@ -322,7 +322,11 @@ def main():
                 clocks=clocks,
                 roofline=dict(kernel="gemm_conv_kernel (tcgen05 implicit-GEMM conv/linear), rank 0", bound="tensor", achieved=achieved,
                               peak=pk["tf_sustained"], unit="TFLOP/s", frac=(achieved / pk["tf_sustained"]) if achieved else None,
-                              traffic=None, peak_source=pk["src"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
+                              traffic=2.42e9 if L == FULL_L and world == 1 and not args.heads else None,
+                              traffic_note="bytes, dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant shape "
+                                           "(conv5 768->768 over 262,144 rows, res + out + actA) from the ncu --set full capture in "
+                                           "profiles/ncu_r01_summary.md section 2; equals that launch's algorithmic bytes (nothing is re-read)",
+                              peak_source=pk["src"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
                               launches_per_step=n_gemm // max(args.steps, 1), share_of_step=gemm_ms / (ms_eager * args.steps),
                               algorithmic_tflop_per_step=gemm_flops / max(args.steps, 1) / 1e12,
                               measured="CUDA events around every launch in %d eagerly launched steps (%.2f ms/step) right after the timed region" % (args.steps, ms_eager)))
