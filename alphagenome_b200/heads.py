@@ -223,40 +223,62 @@ class HeadsEngine:
 
     # ---------------------------------------------------------------------------------------- forward
     @torch.no_grad()
-    def run(self, out: Dict, organism_index, head_kwargs: Dict, sp=None, plan=None):
-        """out: the engine's dict (embeddings fp32 + bf16 copies `embeds_1bp_b16` / `embeds_128bp_b16`)."""
+    def run(self, out: Dict, organism_index, head_kwargs: Dict, sp=None, plan=None, requested_heads=None, track_masks=None):
+        """out: the engine's dict (embeddings fp32 + bf16 copies `embeds_1bp_b16` / `embeds_128bp_b16`; a missing bf16
+        copy — embeddings handed back by the caller, AG:1911 — is made by rounding the fp32 tensor)."""
         model = self.model
         dev = out["embeds_1bp"].device
         P = self.pack(dev)
-        head_inputs = dict(embeds_1bp=out["embeds_1bp"], embeds_128bp=out["embeds_128bp"], embeds_pair=out["embeds_pair"],
-                           organism_index=organism_index, unet_output=out["unet_output"], single_repr=out["single_repr"],
-                           pairwise_repr=out["pairwise_repr"])
+        head_inputs = {k: out[k] for k in ("embeds_1bp", "embeds_128bp", "embeds_pair", "unet_output", "single_repr", "pairwise_repr") if k in out}
+        head_inputs["organism_index"] = organism_index
         assert not set(head_inputs) & set(head_kwargs)                      # AG:1818
         head_inputs.update(head_kwargs)
         head_inputs.setdefault("splice_site_positions", None)
-        b16 = dict(embeds_1bp=out["embeds_1bp_b16"], embeds_128bp=out["embeds_128bp_b16"])
+        b16 = {}
+
+        def operand(name):
+            if name not in b16:
+                t = out.get(name + "_b16")
+                b16[name] = t if t is not None else out[name].to(torch.bfloat16)
+            return b16[name]
+
         result = {}
         for organism, heads in model.heads.items():
             organism_out = {}
             for name, head in heads.items():
+                if requested_heads is not None and name not in requested_heads:      # AG:1941
+                    continue
                 arg_names = model.head_forward_arg_names[organism][name]
                 arg_map = model.head_forward_arg_maps[organism][name]
                 kwargs = {arg_map.get(k, k): head_inputs[k] for k in arg_names}    # AG:1838-1842
                 e = P[(organism, name)]
                 if isinstance(head, TracksScaledPrediction):
                     (src,) = arg_names
-                    organism_out[name] = self.tracks(e, b16[src]) if src in b16 else None
-                    if organism_out[name] is None:
+                    if src not in ("embeds_1bp", "embeds_128bp"):
                         raise ops._lib.AgbError(f"TracksScaledPrediction on {src!r}: only embeds_1bp / embeds_128bp inputs are supported")
+                    pred = self.tracks(e, operand(src))
                 elif isinstance(head, ContactMapHead):
-                    organism_out[name] = self.contact(e, kwargs["embeds_pair"], organism_index)
+                    pred = self.contact(e, kwargs["embeds_pair"], organism_index)
                 elif isinstance(head, SpliceSiteClassifier):
-                    organism_out[name] = self._gemm_out(b16["embeds_1bp"], e)
+                    pred = self._gemm_out(operand("embeds_1bp"), e)
                 elif isinstance(head, SpliceSiteUsage):
-                    organism_out[name] = self._gemm_out(b16["embeds_1bp"], e, ACT_SIGMOID)
+                    pred = self._gemm_out(operand("embeds_1bp"), e, ACT_SIGMOID)
                 elif isinstance(head, SpliceJunctionHead):
-                    organism_out[name] = self.splice_juncs(e, b16["embeds_1bp"], kwargs["splice_donor_idx"], kwargs["splice_acceptor_idx"], sp, plan)
+                    pred = self.splice_juncs(e, operand("embeds_1bp"), kwargs["splice_donor_idx"], kwargs["splice_acceptor_idx"], sp, plan)
                 else:
-                    organism_out[name] = head(**kwargs)   # a user module: called like the reference does (AG:1846)
-            result[organism] = organism_out
+                    pred = head(**kwargs)   # a user module: called like the reference does (AG:1846)
+                if track_masks and name in track_masks:                              # AG:1958-1959
+                    pred = apply_track_mask(pred, track_masks[name])
+                organism_out[name] = pred
+            if organism_out or requested_heads is None:
+                result[organism] = organism_out
         return result
+
+
+def apply_track_mask(head_output, mask):
+    """AlphaGenome._apply_track_mask AG:1967-1987."""
+    if torch.is_tensor(head_output):
+        return head_output[..., mask]
+    if isinstance(head_output, dict):
+        return {k: (v[..., mask] if torch.is_tensor(v) and v.dim() >= 2 else v) for k, v in head_output.items()}
+    return head_output

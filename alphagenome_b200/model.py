@@ -387,19 +387,50 @@ class AlphaGenome(nn.Module):
             return embeds
         return embeds, TransformerUnetOutput(out["unet_output"], out["single_repr"], out["pairwise_repr"])
 
+    def _heads(self):
+        from .heads import HeadsEngine
+
+        if getattr(self, "_heads_engine", None) is None:
+            object.__setattr__(self, "_heads_engine", HeadsEngine(self))
+        return self._heads_engine
+
     @torch.no_grad()
     def forward(self, seq, organism_index, return_embeds=False, **head_kwargs):
         """AG:1780-1852: Embeds when no heads are registered (or return_embeds), else {organism: {head: prediction}}
         with every organism's heads run on every sample."""
         if len(self.heads) == 0 or return_embeds:
             return self.get_embeds(seq, organism_index)
-        from .heads import HeadsEngine
         from .trunk import engine_for
 
         organism_index = self._organism_tensor(seq, organism_index).to(seq.device).long()
         eng = engine_for(self.transformer_unet, self)
         out = eng.run_embeds(seq, organism_index, want_head_operands=True)
-        if getattr(self, "_heads_engine", None) is None:
-            object.__setattr__(self, "_heads_engine", HeadsEngine(self))
         plan = eng.sp.plan(seq.shape[1]) if eng.sp is not None else None
-        return self._heads_engine.run(out, organism_index, head_kwargs, sp=eng.sp, plan=plan)
+        return self._heads().run(out, organism_index, head_kwargs, sp=eng.sp, plan=plan)
+
+    @torch.no_grad()
+    def inference(self, seq, organism_index, *, requested_heads=None, track_masks=None, embeds=None, return_embeds=False,
+                  **head_kwargs):
+        """AG:1853-1965: selective head execution (`requested_heads`), per-head track masks, and reuse of embeddings
+        computed earlier with get_embeds() (`embeds=`; their bf16 MMA operands are then made by rounding)."""
+        from .trunk import engine_for
+
+        organism_index = self._organism_tensor(seq, organism_index).to(seq.device).long()
+        eng = engine_for(self.transformer_unet, self)
+        if embeds is None:
+            out = eng.run_embeds(seq, organism_index, want_head_operands=len(self.heads) != 0)
+            embeds = Embeds(out["embeds_1bp"], out["embeds_128bp"], out["embeds_pair"])
+        else:
+            out = dict(embeds_1bp=embeds[0], embeds_128bp=embeds[1], embeds_pair=embeds[2])
+        if len(self.heads) == 0:
+            return embeds if return_embeds else {}
+        plan = eng.sp.plan(seq.shape[1]) if eng.sp is not None else None
+        res = self._heads().run(out, organism_index, head_kwargs, sp=eng.sp, plan=plan, requested_heads=requested_heads,
+                                track_masks=track_masks)
+        res = {o: h for o, h in res.items() if h}                                   # AG:1963
+        return (res, embeds) if return_embeds else res
+
+    def _apply_track_mask(self, head_output, mask):
+        from .heads import apply_track_mask
+
+        return apply_track_mask(head_output, mask)

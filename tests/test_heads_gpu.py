@@ -85,3 +85,35 @@ def test_custom_head_is_called_like_the_reference():
     out = m(seq, 0)
     emb = m(seq, 0, return_embeds=True)
     assert torch.allclose(out["human"]["mean128"], emb.embeds_128bp.mean(dim=1))
+
+
+def test_inference_matches_forward_and_filters_heads():
+    """Mirrors the reference's tests/test_selective_inference.py:42-146: inference() == forward(), head filtering,
+    track masks, embedding reuse."""
+    case = HEAD_CASES[0]
+    seq, org, donor, acceptor = make_head_inputs(case)
+    model = model_with_heads(case["weight_seed"])
+    kw = dict(splice_donor_idx=donor.cuda(), splice_acceptor_idx=acceptor.cuda())
+    full = model(seq.cuda(), org.cuda(), **kw)
+    inf = model.inference(seq.cuda(), org.cuda(), **kw)
+    for organism in full:
+        for name in full[organism]:
+            assert torch.equal(full[organism][name], inf[organism][name]), (organism, name)
+    # head filtering: only the requested heads run; organisms without any requested head are dropped
+    sel = model.inference(seq.cuda(), org.cuda(), requested_heads={"128bp_tracks", "contact_head"})
+    assert set(sel) == {"human", "mouse"} and set(sel["human"]) == {"128bp_tracks", "contact_head"}
+    assert torch.equal(sel["mouse"]["contact_head"], full["mouse"]["contact_head"])
+    # track masks slice the last dimension
+    mask = torch.tensor([True, False, True, True, False], device="cuda")      # splice_logits has 5 tracks for both organisms
+    masked = model.inference(seq.cuda(), org.cuda(), requested_heads={"splice_logits"}, track_masks={"splice_logits": mask})
+    for organism in ("human", "mouse"):
+        assert torch.equal(masked[organism]["splice_logits"], full[organism]["splice_logits"][..., mask])
+    # embedding reuse: heads on embeddings handed back by the caller (bf16 operands made by rounding the fp32 tensors)
+    emb = model.get_embeds(seq.cuda(), org.cuda())
+    emb = type(emb)(*[t.clone() for t in emb])
+    reused, emb2 = model.inference(seq.cuda(), org.cuda(), embeds=emb, return_embeds=True, requested_heads={"1bp_tracks", "contact_head"})
+    assert emb2 is emb
+    for organism in ("human", "mouse"):
+        for name in ("1bp_tracks", "contact_head"):
+            a, b = reused[organism][name].float(), full[organism][name].float()
+            assert ((a - b).abs().max() / b.abs().max()).item() < 5e-3, (organism, name)
