@@ -170,7 +170,7 @@ def load() -> C.CDLL:
     lib.ag_add_embed_norm_fwd.argtypes = [P] * 6 + [I32] * 3 + [C.c_int, P]
     lib.ag_pair_out_embed_fwd.argtypes = [P] * 6 + [I32] * 4 + [C.c_int, P]
     lib.ag_rmsnorm_act_fwd.argtypes = [P] * 5 + [I64, I64, I32, I32, C.c_int, P]
-    lib.ag_splice_rope_fwd.argtypes = [P] * 6 + [I32] * 5 + [C.c_int, P]
+    lib.ag_splice_rope_fwd.argtypes = [P] * 6 + [I32] * 6 + [C.c_int, P]
     lib.ag_gemm_set_cta_group.argtypes = [C.c_int]
     lib.ag_gemm_set_cta_group.restype = C.c_int
     for name in EXPORTED[6:]:

@@ -228,10 +228,10 @@ int ag_rmsnorm_act_fwd(const float* x, const float* w, const float* b, const flo
 }
 
 int ag_splice_rope_fwd(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
-                       void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t hidden, int32_t p_ld, int device,
-                       void* stream) {
+                       void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t hidden, int32_t p_ld, int32_t tab_per_site,
+                       int device, void* stream) {
   if (int rc = ensure_device(device)) return rc;
-  return launch_splice_rope(x, scale, offset, cos_tab, sin_tab, out_bf16, B, P, T, hidden, p_ld, device,
+  return launch_splice_rope(x, scale, offset, cos_tab, sin_tab, out_bf16, B, P, T, hidden, p_ld, tab_per_site, device,
                             static_cast<cudaStream_t>(stream));
 }
 

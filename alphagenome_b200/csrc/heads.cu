@@ -50,7 +50,7 @@ __global__ void rmsnorm_act_kernel(const float* __restrict__ x, const float* __r
 // with the context index t as the rotary position (AG:1352-1359).  One thread per 4 channels (two rotary pairs).
 __global__ void splice_rope_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ offset,
                                    const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
-                                   __nv_bfloat16* __restrict__ out, int B, int P, int T, int Hd, int p_ld) {
+                                   __nv_bfloat16* __restrict__ out, int B, int P, int T, int Hd, int p_ld, int tab_per_site) {
   const int q4 = Hd / 4;
   const long total = (long)B * T * P * q4;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -63,8 +63,10 @@ __global__ void splice_rope_kernel(const float* __restrict__ x, const float* __r
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + (b * P + p) * (long)Hd) + c4);
     const float4 s = __ldg(reinterpret_cast<const float4*>(scale + (long)t * Hd) + c4);
     const float4 o = __ldg(reinterpret_cast<const float4*>(offset + (long)t * Hd) + c4);
-    const float2 c = __ldg(reinterpret_cast<const float2*>(cos_tab + (long)t * (Hd / 2)) + c4);
-    const float2 sn = __ldg(reinterpret_cast<const float2*>(sin_tab + (long)t * (Hd / 2)) + c4);
+    // rotary position: the context index t (SpliceJunctionHead, AG:1356) or the site itself (SpliceSitesJunctionHead, AG:1495)
+    const long trow = tab_per_site ? b * P + p : (long)t;
+    const float2 c = __ldg(reinterpret_cast<const float2*>(cos_tab + trow * (Hd / 2)) + c4);
+    const float2 sn = __ldg(reinterpret_cast<const float2*>(sin_tab + trow * (Hd / 2)) + c4);
     const float u0 = fmaf(v.x, s.x, o.x), u1 = fmaf(v.y, s.y, o.y), u2 = fmaf(v.z, s.z, o.z), u3 = fmaf(v.w, s.w, o.w);
     uint2 pk;
     pk.x = hpack2(u0 * c.x - u1 * sn.x, u1 * c.x + u0 * sn.x);
@@ -92,11 +94,11 @@ int launch_rmsnorm_act(const float* x, const float* w, const float* b, const flo
 }
 
 int launch_splice_rope(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
-                       void* out, int B, int P, int T, int Hd, int p_ld, int device, cudaStream_t st) {
+                       void* out, int B, int P, int T, int Hd, int p_ld, int tab_per_site, int device, cudaStream_t st) {
   if (!x || !scale || !offset || !cos_tab || !sin_tab || !out) return set_error("ag_splice_rope_fwd: null pointer");
   if (Hd % 8 || B < 1 || P < 1 || T < 1 || p_ld < P) return set_error("ag_splice_rope_fwd: bad sizes (hidden %d must be a multiple of 8, p_ld >= P)", Hd);
   const long total = (long)B * T * P * (Hd / 4);
-  splice_rope_kernel<<<head_grid(total, 256, device), 256, 0, st>>>(x, scale, offset, cos_tab, sin_tab, (__nv_bfloat16*)out, B, P, T, Hd, p_ld);
+  splice_rope_kernel<<<head_grid(total, 256, device), 256, 0, st>>>(x, scale, offset, cos_tab, sin_tab, (__nv_bfloat16*)out, B, P, T, Hd, p_ld, tab_per_site);
   return check_launch("ag_splice_rope_fwd");
 }
 

@@ -52,6 +52,6 @@ int launch_pair_out_embed(const float* pair, const float* pairT, const float* w,
 int launch_rmsnorm_act(const float* x, const float* w, const float* b, const float* add, void* out, long rows,
                        long rows_per_batch, int C, int act, int device, cudaStream_t st);
 int launch_splice_rope(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
-                       void* out, int B, int P, int T, int Hd, int p_ld, int device, cudaStream_t st);
+                       void* out, int B, int P, int T, int Hd, int p_ld, int tab_per_site, int device, cudaStream_t st);
 
 }  // namespace agb

@@ -107,6 +107,63 @@ class SpliceJunctionHead(nn.Module):
         raise RuntimeError("run through AlphaGenome.forward (alphagenome_b200.heads.run_heads)")
 
 
+class GenomeTracksHead(nn.Module):
+    """AG:1395-1423 (JAX-style genome tracks head with per-resolution submodules)."""
+
+    def __init__(self, dim_1bp, dim_128bp, num_tracks, resolutions=(1, 128)):
+        super().__init__()
+        self.resolutions = nn.ModuleDict()
+        if 1 in resolutions:
+            self.resolutions["resolution_1"] = TracksScaledPrediction(dim_1bp, num_tracks)
+        if 128 in resolutions:
+            self.resolutions["resolution_128"] = TracksScaledPrediction(dim_128bp, num_tracks)
+
+    def forward(self, embeds_1bp=None, embeds_128bp=None):
+        raise RuntimeError("run through AlphaGenome.forward (alphagenome_b200.heads.run_heads)")
+
+
+class ContactMapsHead(nn.Module):
+    """AG:1425-1442 (symmetrize + Linear)."""
+
+    def __init__(self, input_dim, num_tracks):
+        super().__init__()
+        self.to_pred = nn.Linear(input_dim, num_tracks)
+
+    def forward(self, embeds_pair, organism_index=None):
+        raise RuntimeError("run through AlphaGenome.forward (alphagenome_b200.heads.run_heads)")
+
+
+class SpliceSitesJunctionHead(nn.Module):
+    """AG:1444-1545 (JAX-style splice junction head: per-site rotary embeddings, positive / negative strand)."""
+
+    def __init__(self, input_dim, hidden_dim, max_num_tissues, rope_max_position=2 ** 20):
+        super().__init__()
+        self.project = nn.Linear(input_dim, hidden_dim)
+        self.hidden_dim, self.max_num_tissues = hidden_dim, max_num_tissues
+        n = 2 * max_num_tissues * hidden_dim
+        self.pos_donor_embeddings = nn.Parameter(torch.zeros(n))
+        self.pos_acceptor_embeddings = nn.Parameter(torch.zeros(n))
+        self.neg_donor_embeddings = nn.Parameter(torch.zeros(n))
+        self.neg_acceptor_embeddings = nn.Parameter(torch.zeros(n))
+        self.rope = _Rope(hidden_dim, max_positions=rope_max_position)
+
+    def forward(self, embeds_1bp, splice_site_positions=None):
+        raise RuntimeError("run through AlphaGenome.forward (alphagenome_b200.heads.run_heads)")
+
+
+# AG:77-90 — the head specs of the official (JAX) checkpoint
+jax_genome_track_heads = {
+    "rna_seq": dict(num_tracks=768, resolutions=(1, 128)), "cage": dict(num_tracks=640, resolutions=(1, 128)),
+    "dnase": dict(num_tracks=384, resolutions=(1, 128)), "procap": dict(num_tracks=128, resolutions=(1, 128)),
+    "atac": dict(num_tracks=256, resolutions=(1, 128)), "chip_tf": dict(num_tracks=1664, resolutions=(128,)),
+    "chip_histone": dict(num_tracks=1152, resolutions=(128,)),
+}
+jax_contact_maps_tracks = 28
+jax_splice_usage_tracks = 734
+jax_splice_junction_hidden_dim = 768
+jax_splice_junction_max_tissues = 367
+
+
 def get_function_arg_names(fn):
     """AG:1262-1265."""
     return [p.name for p in inspect.signature(fn).parameters.values()]
@@ -135,6 +192,13 @@ class HeadsEngine:
             b[:N] = lin.bias.detach().to(device).float()
         return dict(W=W, b=b, N=N, N16=N16)
 
+    def _tracks_pack(self, head, device):
+        e = self._lin(head.to_pred, device)
+        mul = torch.ones(e["N16"], device=device, dtype=torch.float32)
+        mul[: e["N"]] = F.softplus(head.scale.detach().to(device).float())      # AG:1393
+        e["mul"] = mul
+        return e
+
     def pack(self, device):
         key = self._version_key(device)
         if self._pack is not None and self._key == key:
@@ -144,10 +208,18 @@ class HeadsEngine:
             for name, head in heads.items():
                 e: Dict = dict(kind=type(head).__name__)
                 if isinstance(head, TracksScaledPrediction):
+                    e.update(self._tracks_pack(head, device))
+                elif isinstance(head, GenomeTracksHead):
+                    e["res"] = {k: self._tracks_pack(h, device) for k, h in head.resolutions.items()}
+                elif isinstance(head, ContactMapsHead):
                     e.update(self._lin(head.to_pred, device))
-                    mul = torch.ones(e["N16"], device=device, dtype=torch.float32)
-                    mul[: e["N"]] = F.softplus(head.scale.detach().to(device).float())      # AG:1393
-                    e["mul"] = mul
+                elif isinstance(head, SpliceSitesJunctionHead):
+                    e.update(self._lin(head.project, device))
+                    T, Hd = head.max_num_tissues, head.hidden_dim
+                    e.update(T=T, Hd=Hd, inv_freq=head.rope.inv_freq.detach().to(device).float().contiguous())
+                    for nm in ("pos_donor", "pos_acceptor", "neg_donor", "neg_acceptor"):
+                        par = getattr(head, nm + "_embeddings").detach().to(device).float().view(2, T, Hd)     # AG:1489-1491
+                        e[nm] = (par[0].contiguous(), par[1].contiguous())
                 elif isinstance(head, ContactMapHead):
                     e.update(self._lin(head.proj, device))
                     e.update(nw=head.norm.weight.detach().to(device).float().contiguous(), nb=head.norm.bias.detach().to(device).float().contiguous(),
@@ -221,6 +293,51 @@ class HeadsEngine:
         ops.gemm(d.view(B * T, d.shape[2], Hd), a.view(B * T, Pa16, Hd), M=Pd, w_batched=True, actA=Act(scores, None, None, ACT_SOFTPLUS_MUL))
         return scores.view(B, T, Pd, Pa16)[..., :Pa].permute(0, 2, 3, 1)   # 'b d a t'
 
+    def splice_sites_junction(self, e, e1_b16, positions, sp=None, plan=None):
+        """SpliceSitesJunctionHead.forward AG:1501-1545."""
+        if positions is None:
+            return None
+        dev = e1_b16.device
+        B = e1_b16.shape[0]
+        T, Hd = e["T"], e["Hd"]
+        positions = positions.to(dev).long()
+        sharded = sp is not None and plan is not None and plan.world > 1
+
+        def site_embed(idx, par):
+            safe = idx.clamp_min(0)                                                      # AG:1485
+            if sharded:
+                own = (safe >= plan.start) & (safe < plan.end)
+                loc = (safe - plan.start).clamp(0, plan.L_loc - 1)
+            else:
+                own, loc = None, safe
+            rows = torch.gather(e1_b16, 1, loc[:, :, None].expand(-1, -1, e1_b16.shape[2])).contiguous()
+            x = torch.empty(B, idx.shape[1], e["N16"], device=dev, dtype=torch.float32)
+            ops.gemm(rows, e["W"], n_pad=e["N16"], pre_shift=e["b"], out=x)
+            if own is not None:
+                x = sp.all_reduce_sum(x * own[:, :, None].to(x.dtype))
+            ang = safe.to(torch.float32)[:, :, None] * e["inv_freq"][None, None, :]       # rope(safe_indices), AG:1495
+            P = idx.shape[1]
+            out = torch.zeros(B, T, _round_up(P, 16), Hd, device=dev, dtype=torch.bfloat16)
+            ops.splice_rope(x[..., :Hd].contiguous() if e["N16"] != Hd else x, par[0], par[1], ang.cos().contiguous(), ang.sin().contiguous(), out)
+            return out, P
+
+        def counts(didx, aidx, dpar, apar):
+            d, Pd = site_embed(didx, dpar)
+            a, Pa = site_embed(aidx, apar)
+            Pa16 = a.shape[2]
+            scores = torch.empty(B * T, Pd, Pa16, device=dev, dtype=torch.float32)
+            ops.gemm(d.view(B * T, d.shape[2], Hd), a.view(B * T, Pa16, Hd), M=Pd, w_batched=True, actA=Act(scores, None, None, ACT_SOFTPLUS_MUL))
+            c = scores.view(B, T, Pd, Pa16)[..., :Pa].permute(0, 2, 3, 1)                # 'b d a t'
+            mask = (didx >= 0)[:, :, None] & (aidx >= 0)[:, None, :]                     # AG:1523-1524
+            return c * mask[..., None], mask
+
+        pd, pa, nd, na = (positions[:, i] for i in range(4))
+        pos_c, pos_m = counts(pd, pa, e["pos_donor"], e["pos_acceptor"])
+        neg_c, neg_m = counts(nd, na, e["neg_donor"], e["neg_acceptor"])
+        pred = torch.cat((pos_c, neg_c), dim=-1)
+        mask = torch.cat((pos_m[..., None].expand(*pos_m.shape, T), neg_m[..., None].expand(*neg_m.shape, T)), dim=-1)
+        return dict(predictions=pred, splice_site_positions=positions, splice_junction_mask=mask)
+
     # ---------------------------------------------------------------------------------------- forward
     @torch.no_grad()
     def run(self, out: Dict, organism_index, head_kwargs: Dict, sp=None, plan=None, requested_heads=None, track_masks=None):
@@ -257,6 +374,19 @@ class HeadsEngine:
                     if src not in ("embeds_1bp", "embeds_128bp"):
                         raise ops._lib.AgbError(f"TracksScaledPrediction on {src!r}: only embeds_1bp / embeds_128bp inputs are supported")
                     pred = self.tracks(e, operand(src))
+                elif isinstance(head, GenomeTracksHead):                              # AG:1412-1423
+                    pred = {}
+                    if "resolution_1" in e["res"]:
+                        pred["scaled_predictions_1bp"] = self.tracks(e["res"]["resolution_1"], operand("embeds_1bp"))
+                    if "resolution_128" in e["res"]:
+                        pred["scaled_predictions_128bp"] = self.tracks(e["res"]["resolution_128"], operand("embeds_128bp"))
+                elif isinstance(head, ContactMapsHead):
+                    # symmetrize (AG:1440) is the identity on embeds_pair; Linear on its bf16 rounding
+                    ep = kwargs["embeds_pair"]
+                    Bq, rows, Pn, Cq = ep.shape
+                    pred = self._gemm_out(ep.to(torch.bfloat16).view(Bq, rows * Pn, Cq), e).view(Bq, rows, Pn, e["N"])
+                elif isinstance(head, SpliceSitesJunctionHead):
+                    pred = self.splice_sites_junction(e, operand("embeds_1bp"), kwargs.get("splice_site_positions"), sp, plan)
                 elif isinstance(head, ContactMapHead):
                     pred = self.contact(e, kwargs["embeds_pair"], organism_index)
                 elif isinstance(head, SpliceSiteClassifier):

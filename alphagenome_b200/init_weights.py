@@ -47,6 +47,9 @@ def synth_tensor(seed: int, name: str, shape: Tuple[int, ...]) -> np.ndarray:
         return (1.0 + r.uniform(-0.2, 0.2, shape)).astype(np.float32)
     if leaf == "offset":                          # SpliceJunctionHead.offset (AG:1334), init zeros
         return r.uniform(-0.1, 0.1, shape).astype(np.float32)
+    if leaf.endswith("_embeddings") and len(shape) == 1:   # SpliceSitesJunctionHead: [scale | offset] flat (AG:1473-1476)
+        half = shape[0] // 2
+        return np.concatenate([1.0 + r.uniform(-0.2, 0.2, half), r.uniform(-0.1, 0.1, shape[0] - half)]).astype(np.float32)
     if leaf == "weight":
         fan_in = int(np.prod(shape[1:]))
         bound = 1.0 / math.sqrt(fan_in)

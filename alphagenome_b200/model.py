@@ -387,6 +387,23 @@ class AlphaGenome(nn.Module):
             return embeds
         return embeds, TransformerUnetOutput(out["unet_output"], out["single_repr"], out["pairwise_repr"])
 
+    def add_reference_heads(self, organism, genome_track_heads=None, num_tracks_contacts=None, num_splice_usage_tracks=None,
+                            splice_junction_hidden_dim=None, splice_junction_max_tissues=None):
+        """AG:1684-1731: the JAX-aligned heads of the official checkpoint (rna_seq, cage, dnase, procap, atac, chip_tf,
+        chip_histone, contact_maps, splice_sites_{classification,usage,junction})."""
+        from . import heads as H
+
+        genome_track_heads = H.jax_genome_track_heads if genome_track_heads is None else genome_track_heads
+        for head_name, spec in genome_track_heads.items():
+            self.add_head(organism, head_name, H.GenomeTracksHead(dim_1bp=self.dim_1bp, dim_128bp=self.dim_128bp,
+                                                                  num_tracks=spec["num_tracks"], resolutions=spec["resolutions"]))
+        self.add_head(organism, "contact_maps", H.ContactMapsHead(self.dim_contacts, H.jax_contact_maps_tracks if num_tracks_contacts is None else num_tracks_contacts))
+        self.add_head(organism, "splice_sites_classification", H.SpliceSiteClassifier(self.dim_1bp))
+        self.add_head(organism, "splice_sites_usage", H.SpliceSiteUsage(self.dim_1bp, H.jax_splice_usage_tracks if num_splice_usage_tracks is None else num_splice_usage_tracks))
+        self.add_head(organism, "splice_sites_junction", H.SpliceSitesJunctionHead(
+            self.dim_1bp, H.jax_splice_junction_hidden_dim if splice_junction_hidden_dim is None else splice_junction_hidden_dim,
+            H.jax_splice_junction_max_tissues if splice_junction_max_tissues is None else splice_junction_max_tissues))
+
     def _heads(self):
         from .heads import HeadsEngine
 

@@ -371,12 +371,16 @@ def rmsnorm_act(x, w, b, out, add=None, rows_per_batch: Optional[int] = None, ac
 
 
 def splice_rope(x, scale, offset, cos_tab, sin_tab, out) -> None:
-    """ag_splice_rope_fwd: x fp32 [B, P, H]; scale/offset [T, H]; cos/sin [T, H/2]; out bf16 [B, T, >=P, H]."""
+    """ag_splice_rope_fwd: x fp32 [B, P, H]; scale/offset [T, H]; out bf16 [B, T, >=P, H]; cos/sin [T, H/2] (rotary
+    position = context index) or [B, P, H/2] (rotary position = the site)."""
     B, P, Hd = x.shape
     T = scale.shape[0]
     for t, nm in ((x, "x"), (scale, "scale"), (offset, "offset"), (cos_tab, "cos"), (sin_tab, "sin")):
         _f32(t, nm)
-    _require(tuple(scale.shape) == (T, Hd) and tuple(offset.shape) == (T, Hd) and tuple(cos_tab.shape) == (T, Hd // 2) and tuple(sin_tab.shape) == (T, Hd // 2), "scale/offset [T, H], cos/sin [T, H/2]")
+    per_site = cos_tab.dim() == 3
+    want = (B, P, Hd // 2) if per_site else (T, Hd // 2)
+    _require(tuple(scale.shape) == (T, Hd) and tuple(offset.shape) == (T, Hd) and tuple(cos_tab.shape) == want and tuple(sin_tab.shape) == want,
+             "scale/offset [T, H]; cos/sin [T, H/2] or [B, P, H/2]")
     _require(out.dtype == torch.bfloat16 and out.is_contiguous() and out.dim() == 4 and out.shape[0] == B and out.shape[1] == T and out.shape[2] >= P and out.shape[3] == Hd, "out must be bf16 [B, T, >=P, H]")
     _lib.check(_lib.load().ag_splice_rope_fwd(x.data_ptr(), scale.data_ptr(), offset.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), out.data_ptr(),
-                                              B, P, T, Hd, out.shape[2], _dev(x), _stream()))
+                                              B, P, T, Hd, out.shape[2], 1 if per_site else 0, _dev(x), _stream()))

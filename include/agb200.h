@@ -218,12 +218,14 @@ int ag_pair_out_embed_fwd(const float* pair, const float* pairT, const float* w,
 int ag_rmsnorm_act_fwd(const float* x, const float* w, const float* b, const float* add, void* out_bf16, int64_t rows,
                        int64_t rows_per_batch, int32_t C, int32_t act, int device, void* stream);
 
-/* SpliceJunctionHead.tissue_scaled_rope AG:1338-1361: x fp32 [B][P][hidden] (projected splice-site rows),
- * scale/offset fp32 [T][hidden], cos/sin fp32 [T][hidden/2] (rotary position = context index) ->
- * bf16 [B][T][p_ld][hidden] with out[b][t][p] = rope_t(x[b][p] * scale[t] + offset[t]) (rows p >= P untouched) */
+/* SpliceJunctionHead.tissue_scaled_rope AG:1338-1361 / SpliceSitesJunctionHead._apply_rope AG:1478-1499:
+ * x fp32 [B][P][hidden] (projected splice-site rows), scale/offset fp32 [T][hidden] ->
+ * bf16 [B][T][p_ld][hidden] with out[b][t][p] = rope(x[b][p] * scale[t] + offset[t]) (rows p >= P untouched).
+ * Rotary angle tables cos/sin fp32: tab_per_site == 0: [T][hidden/2], position = context index t (AG:1356);
+ * tab_per_site == 1: [B][P][hidden/2], position = the site's genomic index (AG:1495). */
 int ag_splice_rope_fwd(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
-                       void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t hidden, int32_t p_ld, int device,
-                       void* stream);
+                       void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t hidden, int32_t p_ld, int32_t tab_per_site,
+                       int device, void* stream);
 
 /* library / error plumbing */
 int ag_version(void);

@@ -348,3 +348,68 @@ def alphagenome_heads(sd: SD, embeds: dict, organism_index, organisms, splice_do
             o["splice_juncs"] = splice_junction_head(sd, hp + "splice_juncs.", embeds["embeds_1bp"], splice_donor_idx, splice_acceptor_idx)
         out[org] = o
     return out
+
+
+# ---------------------------------------------------------------------------------------------- JAX-aligned heads
+# (`AlphaGenome.add_reference_heads`, AG:1684-1731: the heads of the official checkpoint)
+JAX_GENOME_TRACK_HEADS = {  # AG:77-85
+    "rna_seq": (768, (1, 128)), "cage": (640, (1, 128)), "dnase": (384, (1, 128)), "procap": (128, (1, 128)),
+    "atac": (256, (1, 128)), "chip_tf": (1664, (128,)), "chip_histone": (1152, (128,)),
+}
+
+
+def genome_tracks_head(sd: SD, p: str, embeds_1bp, embeds_128bp):
+    """GenomeTracksHead.forward AG:1395-1423: one TracksScaledPrediction per resolution present in the state_dict."""
+    out = {}
+    if p + "resolutions.resolution_1.scale" in sd:
+        out["scaled_predictions_1bp"] = tracks_scaled_prediction(sd, p + "resolutions.resolution_1.", embeds_1bp)
+    if p + "resolutions.resolution_128.scale" in sd:
+        out["scaled_predictions_128bp"] = tracks_scaled_prediction(sd, p + "resolutions.resolution_128.", embeds_128bp)
+    return out
+
+
+def contact_maps_head(sd: SD, p: str, embeds_pair):
+    """ContactMapsHead.forward AG:1425-1442: symmetrize -> Linear."""
+    return linear(sd, p + "to_pred.", 0.5 * (embeds_pair + embeds_pair.transpose(1, 2)))
+
+
+def splice_sites_junction_head(sd: SD, p: str, embeds_1bp, splice_site_positions):
+    """SpliceSitesJunctionHead.forward AG:1444-1545: rotary position = the genomic index of the site."""
+    x_proj = linear(sd, p + "project.", embeds_1bp)
+    Hd = x_proj.shape[-1]
+    T = sd[p + "pos_donor_embeddings"].numel() // (2 * Hd)
+    inv = rotary_inv_freq(Hd, 2 ** 20)
+    b = torch.arange(x_proj.shape[0])[:, None]
+
+    def apply(idx, param):
+        safe = idx.clamp_min(0)
+        x = x_proj[b, safe]                                              # [B, P, H]
+        par = sd[p + param].view(2, T, Hd)
+        x = x[:, :, None, :] * par[0] + par[1]                           # [B, P, T, H]
+        ang = (safe.float()[..., None] * inv).repeat_interleave(2, dim=-1)[:, :, None, :]
+        return apply_rope(ang, x)
+
+    pd, pa, nd, na = (splice_site_positions[:, i] for i in range(4))
+    pos = F.softplus(torch.einsum("bdth,bath->bdat", apply(pd, "pos_donor_embeddings"), apply(pa, "pos_acceptor_embeddings")))
+    neg = F.softplus(torch.einsum("bdth,bath->bdat", apply(nd, "neg_donor_embeddings"), apply(na, "neg_acceptor_embeddings")))
+    pmask = (pd >= 0)[:, :, None] & (pa >= 0)[:, None, :]
+    nmask = (nd >= 0)[:, :, None] & (na >= 0)[:, None, :]
+    pred = torch.cat((pos * pmask[..., None], neg * nmask[..., None]), dim=-1)
+    mask = torch.cat((pmask[..., None].expand(*pmask.shape, T), nmask[..., None].expand(*nmask.shape, T)), dim=-1)
+    return dict(predictions=pred, splice_site_positions=splice_site_positions, splice_junction_mask=mask)
+
+
+@torch.no_grad()
+def alphagenome_reference_heads(sd: SD, embeds: dict, organism_index, organisms, splice_site_positions=None):
+    """AlphaGenome.forward AG:1780-1852 for heads registered with add_reference_heads."""
+    out = {}
+    for org in organisms:
+        hp = f"heads.{org}."
+        o = {name: genome_tracks_head(sd, hp + name + ".", embeds["embeds_1bp"], embeds["embeds_128bp"]) for name in JAX_GENOME_TRACK_HEADS}
+        o["contact_maps"] = contact_maps_head(sd, hp + "contact_maps.", embeds["embeds_pair"])
+        o["splice_sites_classification"] = linear(sd, hp + "splice_sites_classification.linear.", embeds["embeds_1bp"])
+        o["splice_sites_usage"] = torch.sigmoid(linear(sd, hp + "splice_sites_usage.linear.", embeds["embeds_1bp"]))
+        o["splice_sites_junction"] = (None if splice_site_positions is None else
+                                      splice_sites_junction_head(sd, hp + "splice_sites_junction.", embeds["embeds_1bp"], splice_site_positions))
+        out[org] = o
+    return out

@@ -65,3 +65,24 @@ def make_head_inputs(case):
     acceptor = np.sort(rng.choice(L, size=(B, case["n_sites"]), replace=True), axis=1)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a).astype(np.int64))
     return t(seq), t(org), t(donor), t(acceptor)
+
+
+# JAX-aligned heads (`add_reference_heads`, AG:1684-1731): genome track heads per resolution, contact maps, splice sites
+REF_HEAD_CASES = [
+    dict(name="refheads_B2_L4096", B=2, L=4096, weight_seed=6, n_sites=10),
+]
+
+
+def make_ref_head_inputs(case):
+    """tokens, organism index and splice_site_positions [B, 4, P] (pos donor, pos acceptor, neg donor, neg acceptor;
+    -1 = padding, AG:1503-1508)."""
+    B, L, P = case["B"], case["L"], case["n_sites"]
+    rng = np.random.default_rng(123)
+    seq = rng.integers(0, 4, size=(B, L))
+    org = np.arange(B, dtype=np.int64) % 2
+    pos = np.sort(rng.choice(L, size=(B, 4, P)), axis=-1)
+    pos[0, 0, -2:] = -1
+    pos[1, 3, -3:] = -1
+    pos[1, 1, -1:] = -1
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).astype(np.int64))
+    return t(seq), t(org), t(pos)

@@ -117,3 +117,49 @@ def test_inference_matches_forward_and_filters_heads():
         for name in ("1bp_tracks", "contact_head"):
             a, b = reused[organism][name].float(), full[organism][name].float()
             assert ((a - b).abs().max() / b.abs().max()).item() < 5e-3, (organism, name)
+
+
+# ----------------------------------------------------------------------------------------------- JAX-aligned heads
+from tests.golden_util import REF_HEAD_CASES, make_ref_head_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("case", REF_HEAD_CASES, ids=[c["name"] for c in REF_HEAD_CASES])
+def test_reference_heads_match_reference_golden(case):
+    """add_reference_heads (the heads of the official checkpoint, AG:1684-1731) for both organisms."""
+    g = np.load(GOLD / f"{case['name']}.npz")
+    seq, org, pos = make_ref_head_inputs(case)
+    m = AlphaGenome()
+    for o in ("human", "mouse"):
+        m.add_reference_heads(o)
+    m = m.cuda().eval()
+    apply_synth_weights(m, seed=case["weight_seed"])
+    out = m(seq.cuda(), org.cuda(), splice_site_positions=pos.cuda())
+    torch.cuda.synchronize()
+    flat = {}
+    for organism, heads in out.items():
+        for name, v in heads.items():
+            if isinstance(v, dict):
+                for k, t in v.items():
+                    flat[f"{organism}/{name}.{k}"] = t
+            elif v is not None:
+                flat[f"{organism}/{name}"] = v
+    keys = [k for k in g.files if "/" in k and not k.endswith("__absmax")]
+    assert sorted(flat) == sorted(keys)
+    worst = (0.0, 1.0)
+    for k in keys:
+        got = flat[k].float().cpu()
+        if got.dim() == 3 and got.shape[1] > 96:
+            got = got[:, sample_rows("head", got.shape)]
+        want = g[k]
+        assert tuple(got.shape) == want.shape, (k, tuple(got.shape), want.shape)
+        if k.endswith("splice_site_positions") or k.endswith("splice_junction_mask"):
+            assert np.array_equal(got.numpy(), want), k
+            continue
+        err = np.abs(got.numpy() - want).max() / float(g[k + "__absmax"])
+        r = pearson(got.numpy(), want)
+        worst = (max(worst[0], err), min(worst[1], r))
+        assert r >= 0.999 and err <= 3e-2, (k, err, r)
+    print("reference heads: worst max-rel-err %.4f, min Pearson %.6f" % worst)
+    # without splice_site_positions the junction head returns None (AG:1506-1507)
+    out2 = m.inference(seq.cuda(), org.cuda(), requested_heads={"splice_sites_junction", "contact_maps"})
+    assert out2["human"]["splice_sites_junction"] is None and tuple(out2["mouse"]["contact_maps"].shape) == (2, 2, 2, 28)

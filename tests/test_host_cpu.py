@@ -145,3 +145,17 @@ def test_heads_state_dict_matches_reference():
     assert m.head_forward_arg_names["human"]["splice_juncs"] == ["embeds_1bp", "splice_donor_idx", "splice_acceptor_idx"]
     assert tuple(m.head_forward_arg_names["mouse"]["1bp_tracks"]) == ("embeds_1bp",)
     assert m.head_forward_arg_maps["human"]["1bp_tracks"] == {"embeds_1bp": "x"}
+
+
+def test_reference_heads_state_dict_matches_reference():
+    """add_reference_heads (JAX-aligned heads, AG:1684-1731): same 98 head keys / shapes as the reference."""
+    from alphagenome_b200.model import AlphaGenome
+
+    m = AlphaGenome()
+    for org in ("human", "mouse"):
+        m.add_reference_heads(org)
+    want = dict(line.split(" ", 1) for line in (Path(__file__).resolve().parent / "golden" / "state_dict_keys_ref_heads.txt").read_text().splitlines())
+    got = {k: str(tuple(v.shape)) for k, v in m.state_dict().items() if k.startswith("heads.")}
+    assert got == want and len(got) == 98
+    assert m.head_forward_arg_names["human"]["rna_seq"] == ["embeds_1bp", "embeds_128bp"]
+    assert m.head_forward_arg_names["mouse"]["splice_sites_junction"] == ["embeds_1bp", "splice_site_positions"]

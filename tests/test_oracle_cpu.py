@@ -101,3 +101,45 @@ def test_oracle_heads_match_reference_golden(case):
             assert got.shape == want.shape, (organism, name, got.shape, want.shape)
             err = np.abs(got.numpy() - want).max() / float(g[f"{organism}/{name}__absmax"])
             assert err < 5e-5, (organism, name, err)
+
+
+# ----------------------------------------------------------------------------------------------- JAX-aligned heads
+from tests.golden_util import REF_HEAD_CASES, make_ref_head_inputs  # noqa: E402
+
+
+def flatten_heads(out):
+    flat = {}
+    for organism, heads in out.items():
+        for name, v in heads.items():
+            if isinstance(v, dict):
+                for k, t in v.items():
+                    flat[f"{organism}/{name}.{k}"] = t
+            elif v is not None:
+                flat[f"{organism}/{name}"] = v
+    return flat
+
+
+@pytest.mark.parametrize("case", REF_HEAD_CASES, ids=[c["name"] for c in REF_HEAD_CASES])
+def test_oracle_reference_heads_match_reference_golden(case):
+    """add_reference_heads (the heads of the official checkpoint) for both organisms."""
+    g = np.load(GOLD / f"{case['name']}.npz")
+    seq, org, pos = make_ref_head_inputs(case)
+    assert np.array_equal(g["splice_site_positions"], pos.numpy())
+    shapes = {}
+    for line in (GOLD / "state_dict_keys_ref_heads.txt").read_text().splitlines():
+        m = re.match(r"(\S+) \((.*)\)", line)
+        shapes[m.group(1)] = tuple(int(x) for x in m.group(2).replace(",", " ").split())
+    sd = synth_sd(case["weight_seed"])
+    sd.update(synth_state_dict(shapes, case["weight_seed"]))
+    emb = O.alphagenome_embeds(sd, seq, org)
+    flat = flatten_heads(O.alphagenome_reference_heads(sd, emb, org, ("human", "mouse"), pos))
+    keys = [k for k in g.files if "/" in k and not k.endswith("__absmax")]
+    assert sorted(flat) == sorted(keys)
+    for k in keys:
+        got = flat[k].float()
+        if got.dim() == 3 and got.shape[1] > 96:
+            got = got[:, sample_rows("head", got.shape)]
+        want = g[k]
+        assert tuple(got.shape) == want.shape, (k, tuple(got.shape), want.shape)
+        err = np.abs(got.numpy() - want).max() / float(g[k + "__absmax"])
+        assert err < 5e-5, (k, err)
