@@ -159,3 +159,37 @@ def test_reference_heads_state_dict_matches_reference():
     assert got == want and len(got) == 98
     assert m.head_forward_arg_names["human"]["rna_seq"] == ["embeds_1bp", "embeds_128bp"]
     assert m.head_forward_arg_names["mouse"]["splice_sites_junction"] == ["embeds_1bp", "splice_site_positions"]
+
+
+def test_heads_engine_packs_padded_bf16_weights_on_cpu():
+    """HeadsEngine.pack is host logic: every Linear becomes a bf16 [1, N, K] operand plus a bias padded to a multiple of
+    16 (the kernels compute 16-padded outputs and return the [..., :N] view); softplus(scale) is folded once."""
+    import torch.nn.functional as F
+
+    from alphagenome_b200.heads import HeadsEngine
+    from alphagenome_b200.init_weights import apply_synth_weights
+    from alphagenome_b200.model import AlphaGenome, publication_heads_config
+
+    m = AlphaGenome()
+    m.add_heads(**publication_heads_config["mouse"])
+    apply_synth_weights(m, seed=2)
+    P = HeadsEngine(m).pack(torch.device("cpu"))
+    e = P[("mouse", "1bp_tracks")]
+    head = m.heads["mouse"]["1bp_tracks"]
+    assert e["N"] == 730 and e["N16"] == 736 and tuple(e["W"].shape) == (1, 730, 1536) and e["W"].dtype == torch.bfloat16
+    assert torch.equal(e["b"][:730], head.to_pred.bias.detach()) and torch.all(e["b"][730:] == 0)
+    assert torch.allclose(e["mul"][:730], F.softplus(head.scale.detach())) and torch.all(e["mul"][730:] == 1)
+    sj = P[("mouse", "splice_juncs")]
+    assert sj["T"] == 75 and sj["Hd"] == 512 and tuple(sj["cos"].shape) == (75, 256)
+    # rotary position = context index (AG:1356): angle[t, j] = t * inv_freq[j]
+    inv = m.heads["mouse"]["splice_juncs"].rope.inv_freq
+    assert torch.allclose(sj["cos"][3], torch.cos(3.0 * inv)) and torch.allclose(sj["sin"][74], torch.sin(74.0 * inv))
+    ch = P[("mouse", "contact_head")]
+    assert ch["N"] == 8 and ch["N16"] == 16 and tuple(ch["emb"].shape) == (2, 128)
+    # a second pack with unchanged parameters is the cached object; an in-place update invalidates it
+    eng = HeadsEngine(m)
+    p1 = eng.pack(torch.device("cpu"))
+    assert eng.pack(torch.device("cpu")) is p1
+    with torch.no_grad():
+        head.scale.add_(1.0)
+    assert eng.pack(torch.device("cpu")) is not p1
