@@ -177,7 +177,19 @@ def gemm(
         e0.record()
         _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
         e1.record()
-        PROFILE_GEMM.append((e0, e1, 2.0 * batch * M * (w_rows or N) * K * taps))
+        # algorithmic bytes of this launch: every operand / output once at its storage dtype
+        def _out_bytes(a, rows):
+            return 0 if a is None else batch * rows * N * a.dst.element_size()
+
+        nbytes = (batch if not (w_batched and A.shape[0] == 1) else 1) * a_rows * K * 2 + W.numel() * 2
+        if res is not None:
+            nbytes += batch * (((M - 1) >> res_shift) + 1) * g.res_ch * 4
+        if out is not None:
+            nbytes += batch * M * N * 4
+        if pool is not None:
+            nbytes += batch * (M // 2) * N * 4
+        nbytes += _out_bytes(actA, M) + _out_bytes(actB, M) + _out_bytes(actP, M // 2)
+        PROFILE_GEMM.append((e0, e1, 2.0 * batch * M * (w_rows or N) * K * taps, float(nbytes)))
         return
     _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
 

@@ -292,9 +292,19 @@ def main():
     ms_eager = p0.elapsed_time(p1) / args.steps
     prof = ops.PROFILE_GEMM
     ops.PROFILE_GEMM = None
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    gemm_flops = sum(f for _, _, f in prof)
+    times = [a.elapsed_time(b) for a, b, _, _ in prof]
+    gemm_ms = sum(times)
+    gemm_flops = sum(f for _, _, f, _ in prof)
     n_gemm = len(prof)
+    # the same launches split by arithmetic intensity against the machine's ridge point (sustained bf16 peak / HBM peak):
+    # convs and wide linears are tensor-bound, the K <= 128 pair linears / w1 convs / embedding GEMMs are HBM-bound
+    pk0 = peaks()
+    ridge = pk0["tf_sustained"] * 1e12 / (pk0["hbm"] * 1e9)
+    t_ms = sum(t for t, (_, _, f, nb) in zip(times, prof) if f / nb >= ridge)
+    t_fl = sum(f for _, _, f, nb in prof if f / nb >= ridge)
+    h_ms = sum(t for t, (_, _, f, nb) in zip(times, prof) if f / nb < ridge)
+    h_by = sum(nb for _, _, f, nb in prof if f / nb < ridge)
+    n_tensor = sum(1 for _, _, f, nb in prof if f / nb >= ridge)
 
     tms = torch.tensor([ms, ms_e2e, ms_eager], device=dev, dtype=torch.float64)
     if world > 1:
@@ -329,6 +339,16 @@ def main():
                               peak_source=pk["src"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
                               launches_per_step=n_gemm // max(args.steps, 1), share_of_step=gemm_ms / (ms_eager * args.steps),
                               algorithmic_tflop_per_step=gemm_flops / max(args.steps, 1) / 1e12,
+                              by_bound=dict(
+                                  ridge_flop_per_byte=ridge,
+                                  tensor_bound=dict(launches_per_step=n_tensor // max(args.steps, 1), share_of_gemm_time=t_ms / gemm_ms if gemm_ms else None,
+                                                    achieved_tflops=t_fl / (t_ms * 1e-3) / 1e12 if t_ms else None,
+                                                    frac=t_fl / (t_ms * 1e-3) / 1e12 / pk["tf_sustained"] if t_ms else None),
+                                  hbm_bound=dict(launches_per_step=(n_gemm - n_tensor) // max(args.steps, 1), share_of_gemm_time=h_ms / gemm_ms if gemm_ms else None,
+                                                 achieved_gbs=h_by / (h_ms * 1e-3) / 1e9 if h_ms else None,
+                                                 frac=h_by / (h_ms * 1e-3) / 1e9 / pk["hbm"] if h_ms else None,
+                                                 note="algorithmic bytes (each operand / output once); eager launches, so the many "
+                                                      "sub-100 us pair linears also carry their launch gaps")),
                               measured="CUDA events around every launch in %d eagerly launched steps (%.2f ms/step) right after the timed region" % (args.steps, ms_eager)))
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1

@@ -40,7 +40,7 @@ e1.record()
 torch.cuda.synchronize()
 total = e0.elapsed_time(e1)
 rows = []
-for (a, b, fl), (sa, sw, wb, outs) in zip(ops.PROFILE_GEMM, shapes):
+for (a, b, fl, _nb), (sa, sw, wb, outs) in zip(ops.PROFILE_GEMM, shapes):
     ms = a.elapsed_time(b)
     rows.append(dict(A=sa, W=sw, batched=wb, outs=outs, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1), gflop=round(fl / 1e9, 2)))
 gsum = sum(r["ms"] for r in rows)
