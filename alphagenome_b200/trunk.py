@@ -69,6 +69,18 @@ class TrunkEngine:
         if self._pack is not None and self._pack_key == key:
             return self._pack
         unet = self.unet()
+        if not getattr(self, "_warned_frozen", False):
+            # The reference's BatchRMSNorm re-estimates running_var from the batch on EVERY forward unless it is frozen
+            # (update_running_var defaults to True, AG:331; its inference tests call set_update_running_var(model, False)).
+            # The B200 forward always normalises with the stored running_var and never modifies it.
+            mods = [unet] + ([self.model()] if self.model is not None and self.model() is not None else [])
+            if any(getattr(m, "update_running_var", False) for root in mods for m in root.modules() if type(m).__name__ == "BatchRMSNorm"):
+                import warnings
+
+                warnings.warn("alphagenome_b200 runs BatchRMSNorm with frozen statistics (the stored running_var is used and "
+                              "never updated); call set_update_running_var(model, False) on the reference model for identical behaviour",
+                              stacklevel=3)
+            self._warned_frozen = True
         if device.type != "cuda" and not getattr(self, "_allow_cpu_pack", False):  # (tests pack on CPU to compare layouts)
             raise ops._lib.AgbError("alphagenome_b200 runs only on a CUDA (sm_100a) device; move the model and inputs to cuda")
         f32 = dict(device=device, dtype=torch.float32)
