@@ -50,6 +50,7 @@ struct AttnKParams {
   CUtensorMap tmV;   // (keys, dv, kv_heads, batch)
   AgAttnArgs a;
   int q_tiles, nblk;
+  int tile_off;        // first tile of this launch (a call may be issued as a full-wave launch + a key-split tail launch)
   unsigned int* err;
 };
 
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tile = kSplit == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile = p.tile_off + (kSplit == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
   const uint32_t crank = kSplit == 2 ? cluster_ctarank() : 0u;
   const int qt = tile % p.q_tiles;
   const int h = (tile / p.q_tiles) % a.heads;
@@ -543,50 +544,66 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
     if (int rc = make_tensor_map_bf16(&p.tmV, a.Vt, 4, dims, str, box)) return rc;
   }
   // key split: two CTAs per tile when that shortens the schedule (waves x blocks per CTA; the DSMEM combine costs about
-  // 6 blocks' worth: measured 0.371 -> 0.385 ms at 512 tiles x 64 blocks, 0.098 -> 0.063 ms at 64 tiles x 64 blocks)
+  // 6 blocks' worth: measured 0.371 -> 0.385 ms at 512 tiles x 64 blocks, 0.098 -> 0.063 ms at 64 tiles x 64 blocks).
+  // With more tiles than SMs the full waves run unsplit and only a last partial wave of <= sms/2 tiles is split, so that
+  // it costs about half a wave instead of a whole one.
   const long tiles = (long)p.q_tiles * a.heads * a.batch;
   if (tiles > 1073741823L) return set_error("ag_attention_fwd: grid too large");
   const int sms = sm_count(device);
-  int split = 1;
+  long n_plain = tiles, n_split = 0;
   if (a.mode == 0 && p.nblk >= 2 && a.norm_out == nullptr) {
-    const long t1 = ((tiles + sms - 1) / sms) * (long)p.nblk;
-    const long t2 = ((2 * tiles + sms - 1) / sms) * (long)((p.nblk + 1) / 2 + 6);
-    if (t2 < t1) split = 2;
+    const long cost_split = (p.nblk + 1) / 2 + 6;
+    if (tiles * 2 <= sms) {
+      if (cost_split < p.nblk) { n_plain = 0; n_split = tiles; }
+    } else if (tiles > sms) {
+      const long tail = tiles % sms;
+      if (tail > 0 && tail * 2 <= sms && cost_split < p.nblk) { n_plain = tiles - tail; n_split = tail; }
+    }
     const char* e = getenv("AGB_ATTN_SPLIT");
-    if (e && (e[0] == '1' || e[0] == '2')) split = e[0] - '0';
+    if (e && e[0] == '1') { n_plain = tiles; n_split = 0; }
+    if (e && e[0] == '2') { n_plain = 0; n_split = tiles; }
   }
-  void (*fn)(const AttnKParams) = nullptr;
-  int slot = 0;
-  switch (attn_poly_of8()) {
-    case 0: fn = split == 2 ? attention_kernel<0, 2> : attention_kernel<0, 1>; slot = 0; break;
-    case 4: fn = split == 2 ? attention_kernel<4, 2> : attention_kernel<4, 1>; slot = 2; break;
-    case 5: fn = split == 2 ? attention_kernel<5, 2> : attention_kernel<5, 1>; slot = 3; break;
-    case 6: fn = split == 2 ? attention_kernel<6, 2> : attention_kernel<6, 1>; slot = 4; break;
-    default: fn = split == 2 ? attention_kernel<2, 2> : attention_kernel<2, 1>; slot = 1; break;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int split = pass == 0 ? 1 : 2;
+    const long ntile = pass == 0 ? n_plain : n_split;
+    if (ntile == 0) continue;
+    p.tile_off = pass == 0 ? 0 : (int)n_plain;
+    void (*fn)(const AttnKParams) = nullptr;
+    int slot = 0;
+    switch (attn_poly_of8()) {
+      case 0: fn = split == 2 ? attention_kernel<0, 2> : attention_kernel<0, 1>; slot = 0; break;
+      case 4: fn = split == 2 ? attention_kernel<4, 2> : attention_kernel<4, 1>; slot = 2; break;
+      case 5: fn = split == 2 ? attention_kernel<5, 2> : attention_kernel<5, 1>; slot = 3; break;
+      case 6: fn = split == 2 ? attention_kernel<6, 2> : attention_kernel<6, 1>; slot = 4; break;
+      default: fn = split == 2 ? attention_kernel<2, 2> : attention_kernel<2, 1>; slot = 1; break;
+    }
+    static thread_local unsigned char attr_done[64][2][5];
+    if (!attr_done[device][split - 1][slot]) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+      if (e != cudaSuccess) return set_error("ag_attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_done[device][split - 1][slot] = 1;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(ntile * split), 1, 1);
+    cfg.blockDim = dim3(kAttThreads, 1, 1);
+    cfg.dynamicSmemBytes = kAttSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)split;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
+    if (le != cudaSuccess) return set_error("ag_attention_fwd: launch failed: %s", cudaGetErrorString(le));
+    if (pass == 0 && n_split > 0) {
+      if (int rc = check_launch("ag_attention_fwd")) return rc;
+    }
   }
-  static thread_local unsigned char attr_done[64][2][5];
-  if (!attr_done[device][split - 1][slot]) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
-    if (e != cudaSuccess) return set_error("ag_attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_done[device][split - 1][slot] = 1;
-  }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(tiles * split), 1, 1);
-  cfg.blockDim = dim3(kAttThreads, 1, 1);
-  cfg.dynamicSmemBytes = kAttSmem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)split;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
-  if (le != cudaSuccess) return set_error("ag_attention_fwd: launch failed: %s", cudaGetErrorString(le));
   return check_launch("ag_attention_fwd");
 }
 
