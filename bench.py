@@ -27,7 +27,7 @@ import torch  # noqa: E402
 METRIC = "trunk_forward_bp_per_s"
 UNIT = "bp/s"
 FULL_L = 1_048_576
-CPU_SAMPLE_L = 131_072
+CPU_SAMPLE_L = int(os.environ.get("AGB_BENCH_CPU_SAMPLE_BP", 131_072))   # the CPU arms time a bounded window of the workload
 
 
 def peaks():

@@ -193,3 +193,27 @@ def test_heads_engine_packs_padded_bf16_weights_on_cpu():
     with torch.no_grad():
         head.scale.add_(1.0)
     assert eng.pack(torch.device("cpu")) is not p1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys.
+    The sample window is shrunk through AGB_BENCH_CPU_SAMPLE_BP so the test stays short."""
+    import json
+    import os
+    import sys
+
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, AGB_BENCH_CPU_SAMPLE_BP="4096")
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "trunk_forward_bp_per_s" and line["unit"] == "bp/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "4096" in line["cpu_baseline"]["sample"]
+    assert line["e2e"] == dict(value=line["value"], unit="bp/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert "workload" in line["config"]
+    # ranks other than 0 of a torchrun launch exit 0 without work
+    r2 = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
+                        env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=120)
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
