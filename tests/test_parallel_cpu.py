@@ -61,6 +61,26 @@ def _worker(rank, world, port, q):
         for s in range(world):
             want = pair[:, s * Pl:(s + 1) * Pl, rank * Pl:(rank + 1) * Pl]
             ok &= torch.equal(pT[s], want)
+        # two tensors of different dtype / width packed into ONE halo collective (decoder input: fp32 residual + bf16 operand)
+        mine16 = (mine[..., :2] * 0.5).to(torch.bfloat16).contiguous()
+        (l32, r32), (l16, r16) = sp.exchange_halos([mine, mine16], 2)
+        if rank > 0:
+            ok &= torch.equal(l32, full[:, rank * rows - 2:rank * rows])
+            ok &= torch.equal(l16, (full[:, rank * rows - 2:rank * rows, :2] * 0.5).to(torch.bfloat16))
+        else:
+            ok &= l32 is None and l16 is None
+        if rank < world - 1:
+            ok &= torch.equal(r16, (full[:, (rank + 1) * rows:(rank + 1) * rows + 2, :2] * 0.5).to(torch.bfloat16))
+        else:
+            ok &= r32 is None and r16 is None
+        # masked sum over ranks (splice-junction head: each gathered site row is owned by exactly one rank)
+        owned = torch.zeros(B, 4, 3)
+        owned[:, rank::world] = float(rank + 1)
+        tot = sp.all_reduce_sum(owned)
+        want_tot = torch.zeros(B, 4, 3)
+        for r in range(world):
+            want_tot[:, r::world] = float(r + 1)
+        ok &= torch.equal(tot, want_tot)
         q.put((rank, bool(ok), sp.n_collectives))
     finally:
         dist.destroy_process_group()
@@ -79,7 +99,7 @@ def test_collectives_world2_gloo():
         p.join(timeout=60)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), res
-    assert all(r[2] == 3 for r in res)
+    assert all(r[2] == 5 for r in res)   # gather, halo, transpose, packed halos, all-reduce
 
 
 def test_halo_window_scheme_is_exact_for_the_conv_stacks():
