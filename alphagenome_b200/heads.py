@@ -30,6 +30,33 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _gemm_n_tile(n: int) -> int:
+    """The N tile ag_gemm_fwd picks for an output width n (multiple of 16): the largest multiple of 16 <= 256 dividing n."""
+    for t in range(256, 15, -16):
+        if n % t == 0:
+            return t
+    return 0
+
+
+def _padded_width(n: int) -> int:
+    """Output width the head GEMM is run at: n rounded up to 16, or further to a multiple of 64 / 128 / 256 when that buys
+    a wider MMA tile (e.g. 730 tracks: 736 = 23 x 32 would run 32-wide tiles, 768 runs 256-wide ones; 3165: 3168 =
+    18 x 176 vs 3328 = 13 x 256).  Cost model (operand ingest): a t-wide tile of a CTA pair needs
+    (16384 + 64 t) bytes per 2 t tensor cycles and levels off at ~53 B/clk of L2 -> smem ingest; 256-wide tiles run at
+    ~0.77 of the full tensor rate."""
+    def eff(t):
+        return min(1.0, 53.0 / (0.77 * (16384 + 64 * t) / (2 * t)))
+
+    best = _round_up(n, 16)
+    best_cost = best / eff(_gemm_n_tile(best))
+    for m in (64, 128, 256):
+        cand = _round_up(n, m)
+        cost = cand / eff(_gemm_n_tile(cand))
+        if cost < 0.97 * best_cost:          # only pad further for a clear win (the padding also costs output memory)
+            best, best_cost = cand, cost
+    return best
+
+
 # --------------------------------------------------------------------------------------------- parameter holders
 class TracksScaledPrediction(nn.Module):
     """AG:1378-1393."""
@@ -185,7 +212,7 @@ class HeadsEngine:
     def _lin(lin: nn.Linear, device):
         """Linear -> (bf16 [1, N, K], fp32 bias padded to a multiple of 16, N, N16)."""
         N, K = lin.weight.shape
-        N16 = _round_up(N, 16)
+        N16 = _padded_width(N)
         W = lin.weight.detach().to(device).to(torch.bfloat16).contiguous().unsqueeze(0)
         b = torch.zeros(N16, device=device, dtype=torch.float32)
         if lin.bias is not None:

@@ -176,7 +176,8 @@ def test_heads_engine_packs_padded_bf16_weights_on_cpu():
     P = HeadsEngine(m).pack(torch.device("cpu"))
     e = P[("mouse", "1bp_tracks")]
     head = m.heads["mouse"]["1bp_tracks"]
-    assert e["N"] == 730 and e["N16"] == 736 and tuple(e["W"].shape) == (1, 730, 1536) and e["W"].dtype == torch.bfloat16
+    # 730 tracks run at width 768 (256-wide MMA tiles) instead of 736 = 23 x 32 (heads._padded_width)
+    assert e["N"] == 730 and e["N16"] == 768 and tuple(e["W"].shape) == (1, 730, 1536) and e["W"].dtype == torch.bfloat16
     assert torch.equal(e["b"][:730], head.to_pred.bias.detach()) and torch.all(e["b"][730:] == 0)
     assert torch.allclose(e["mul"][:730], F.softplus(head.scale.detach())) and torch.all(e["mul"][730:] == 1)
     sj = P[("mouse", "splice_juncs")]
@@ -186,6 +187,10 @@ def test_heads_engine_packs_padded_bf16_weights_on_cpu():
     assert torch.allclose(sj["cos"][3], torch.cos(3.0 * inv)) and torch.allclose(sj["sin"][74], torch.sin(74.0 * inv))
     ch = P[("mouse", "contact_head")]
     assert ch["N"] == 8 and ch["N16"] == 16 and tuple(ch["emb"].shape) == (2, 128)
+    from alphagenome_b200.heads import _gemm_n_tile, _padded_width
+
+    assert (_padded_width(3165), _gemm_n_tile(3328)) == (3328, 256) and _padded_width(2733) == 2816 and _padded_width(282) == 288
+    assert _padded_width(1152) == 1152 and _padded_width(768) == 768 and _padded_width(5) == 16
     # a second pack with unchanged parameters is the cached object; an in-place update invalidates it
     eng = HeadsEngine(m)
     p1 = eng.pack(torch.device("cpu"))
