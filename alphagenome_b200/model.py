@@ -421,9 +421,19 @@ class AlphaGenome(nn.Module):
 
         organism_index = self._organism_tensor(seq, organism_index).to(seq.device).long()
         eng = engine_for(self.transformer_unet, self)
-        out = eng.run_embeds(seq, organism_index, want_head_operands=True)
-        plan = eng.sp.plan(seq.shape[1]) if eng.sp is not None else None
-        return self._heads().run(out, organism_index, head_kwargs, sp=eng.sp, plan=plan)
+
+        def trunk_and_heads(seq, org, **kw):
+            out = eng.run_embeds(seq, org, want_head_operands=True)
+            plan = eng.sp.plan(seq.shape[1]) if eng.sp is not None else None
+            return self._heads().run(out, org, kw, sp=eng.sp, plan=plan)
+
+        if self.cuda_graphs and all(torch.is_tensor(v) for v in head_kwargs.values()):
+            # trunk + every registered head as ONE graph replay (static inputs: tokens, organism index, head kwargs)
+            self._heads().pack(seq.device)
+            kw = {k: v.to(seq.device) for k, v in head_kwargs.items()}
+            return eng.run_graphed(("forward+heads", self._heads()._version_key(seq.device)), lambda seq, org, **kw: trunk_and_heads(seq, org, **kw),
+                                   dict(seq=seq.to(torch.int64), org=organism_index, **kw))
+        return trunk_and_heads(seq, organism_index, **head_kwargs)
 
     @torch.no_grad()
     def inference(self, seq, organism_index, *, requested_heads=None, track_masks=None, embeds=None, return_embeds=False,

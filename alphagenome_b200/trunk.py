@@ -48,21 +48,23 @@ class TrunkEngine:
         self.model = None
         self._pack: Optional[Dict] = None
         self._pack_key = None
+        self._tensors = None   # (model, [parameters and buffers]) the version key walks
         self._rope: Dict = {}
         self._rel: Dict = {}
         self.collect = None  # optional callback(name, tensor) for per-stage parity tests
         self.sp = None       # alphagenome_b200.parallel.SeqParallel when the context is sharded over ranks
-        self._graphs: Dict = {}
+        self._graphs: Dict = {}          # insertion order = least recently used first
+        self.graph_pool_budget = 0.6     # fraction of device memory the kept graphs' pools may hold
 
     # ------------------------------------------------------------------------------------------ packing
     def _version_key(self, device):
-        unet = self.unet()
-        mods = [unet] + ([self.model()] if self.model is not None and self.model() is not None else [])
-        key = [str(device)]
-        for m in mods:
-            for t in list(m.parameters()) + list(m.buffers()):
-                key.append((t.data_ptr(), t._version))
-        return tuple(key)
+        """(data_ptr, _version) of every parameter / buffer: repacks after load_state_dict, .to(), or an in-place update
+        of a parameter.  Updates made through `.data` do not bump `_version` — call invalidate() after those."""
+        model = self.model() if self.model is not None else None
+        if self._tensors is None or self._tensors[0] is not model:
+            mods = [self.unet()] + ([model] if model is not None else [])
+            self._tensors = (model, [t for m in mods for t in list(m.parameters()) + list(m.buffers())])
+        return (str(device),) + tuple((t.data_ptr(), t._version) for t in self._tensors[1])
 
     def pack(self, device) -> Dict:
         key = self._version_key(device)
@@ -175,6 +177,7 @@ class TrunkEngine:
             P["org"] = vec(model.organism_embed.embed.weight)
         self._pack, self._pack_key = P, key
         self._rel.clear()
+        self._rope.clear()
         return P
 
     def rope_tables(self, n: int, device, offset: int = 0):
@@ -485,34 +488,53 @@ class TrunkEngine:
                 out.update(embeds_1bp_b16=e1_b16)
         return out
 
-    def run_embeds_graphed(self, seq, organism_index):
-        """Same as run_embeds, replayed from a CUDA graph (one per input shape): removes the ~190 per-launch host
-        round trips, which matter once a rank's share of the forward is only a few ms.  The returned tensors are
-        the graph's static outputs — they are overwritten by the next call with the same shape."""
-        key = (tuple(seq.shape), str(seq.device), self.sp is not None, self._version_key(seq.device))
-        ent = self._graphs.get(key)
+    def run_graphed(self, tag, fn, tensors: Dict[str, torch.Tensor]):
+        """Replay `fn(**tensors)` from a CUDA graph.  One graph per (tag, input shapes / dtypes, parameter version);
+        the most recently used graphs are kept (alternating shapes — ISM windows, two-pass splice flows — do not
+        re-capture) until their private pools exceed `graph_pool_budget` of the device memory.  The returned tensors are
+        the graph's static outputs: the next call with the same key overwrites them."""
+        dev = next(iter(tensors.values())).device
+        key = (tag, tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())), str(dev), self.sp is not None,
+               self._version_key(dev))
+        ent = self._graphs.pop(key, None)
         if ent is None:
             if self.collect is not None:
                 raise ops._lib.AgbError("stage collection is not available under CUDA graphs")
-            s_seq = seq.to(torch.int64).clone()
-            s_org = organism_index.to(seq.device).long().clone()
-            stream = torch.cuda.Stream(device=seq.device)
+            static = {k: v.clone() for k, v in tensors.items()}
+            stream = torch.cuda.Stream(device=dev)
             stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(stream):
-                self.run_embeds(s_seq, s_org)  # warm-up on the side stream: builds the pack / rope / rel caches
+                fn(**static)  # warm-up on the side stream: builds the pack / rope / rel caches
             torch.cuda.current_stream().wait_stream(stream)
             torch.cuda.synchronize()
+            torch.cuda.empty_cache()   # the warm-up's blocks would otherwise sit cached next to the graph's private pool
+            before = torch.cuda.memory_reserved(dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                out = self.run_embeds(s_seq, s_org)
-            self._graphs.clear()  # one shape at a time keeps the private pool bounded
-            ent = (g, s_seq, s_org, out)
-            self._graphs[key] = ent
-        g, s_seq, s_org, out = ent
-        s_seq.copy_(seq, non_blocking=True)
-        s_org.copy_(organism_index, non_blocking=True)
-        g.replay()
-        return out
+                out = fn(**static)
+            ent = dict(graph=g, static=static, out=out, bytes=max(torch.cuda.memory_reserved(dev) - before, 0))
+            budget = self.graph_pool_budget * torch.cuda.get_device_properties(dev).total_memory
+            while self._graphs and sum(e["bytes"] for e in self._graphs.values()) + ent["bytes"] > budget:
+                self._graphs.pop(next(iter(self._graphs)))   # least recently used first
+        self._graphs[key] = ent      # (re-)inserted last = most recently used
+        for k, v in tensors.items():
+            ent["static"][k].copy_(v, non_blocking=True)
+        ent["graph"].replay()
+        return ent["out"]
+
+    def run_embeds_graphed(self, seq, organism_index):
+        """run_embeds replayed from a CUDA graph: removes the ~190 per-launch host round trips, which matter once a
+        rank's share of the forward is only a few ms."""
+        return self.run_graphed("embeds", lambda seq, org: self.run_embeds(seq, org),
+                                dict(seq=seq.to(torch.int64), org=organism_index.to(seq.device).long()))
+
+    def invalidate(self):
+        """Drop the packed weights, tables and captured graphs (call after changing weights through `.data`, which
+        does not bump the parameter version the caches are keyed on)."""
+        self._pack = self._pack_key = self._tensors = None
+        self._rope.clear()
+        self._rel.clear()
+        self._graphs.clear()
 
     def run_trunk(self, seq, pre_attend_embed=None):
         return self.run(seq, pre_attend_embed, with_embeds=False)

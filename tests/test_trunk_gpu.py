@@ -142,13 +142,54 @@ def test_host_pipeline_matches_direct_calls():
         emb = model(tok.cuda(), org.cuda())
         want.append((emb.embeds_128bp.cpu().clone(), emb.embeds_pair.cpu().clone()))
     got = {}
-    pipe = HostPipeline(model)
+    pipe = HostPipeline(model, outputs=("embeds_128bp", "embeds_pair"))
     n = pipe.run(iter(batches), consume=lambda i, outs: got.__setitem__(i, [o.clone() for o in outs]))
     torch.cuda.synchronize()
     assert n == 5 and sorted(got) == list(range(5))
     for i in range(5):
         assert torch.equal(got[i][0], want[i][0]) and torch.equal(got[i][1], want[i][1])
     assert pipe.d2h_bytes == 5 * sum(t.numel() * 4 for t in want[0])
+    # default: EVERYTHING the call returns is read back (the three embeddings, fp32)
+    full = HostPipeline(model)
+    got3 = {}
+    full.run(iter(batches[:3]), consume=lambda i, outs: got3.__setitem__(i, [o.clone() for o in outs]))
+    assert full.names == ["embeds_1bp", "embeds_128bp", "embeds_pair"]
+    for i in range(3):
+        assert tuple(got3[i][0].shape) == (1, 4096, 1536)
+        assert torch.equal(got3[i][1], want[i][0]) and torch.equal(got3[i][2], want[i][1])
+    assert full.d2h_bytes == 3 * sum(t.numel() * 4 for t in got3[0])
+
+
+def test_alternating_shapes_keep_their_graphs_and_heads_forward_is_graphed():
+    """ISM-style alternating shapes replay their own captured graphs (no re-capture), and the forward WITH heads
+    replays from one graph too and equals the eager forward bit for bit."""
+    from alphagenome_b200.model import publication_heads_config
+
+    model = AlphaGenome()
+    model.add_heads(**publication_heads_config["mouse"])
+    model = model.cuda().eval()
+    apply_synth_weights(model, seed=2)
+    eng = engine_for(model.transformer_unet, model)
+    rng = np.random.default_rng(8)
+    a = torch.from_numpy(rng.integers(0, 4, size=(1, 2048))).cuda()
+    b = torch.from_numpy(rng.integers(0, 4, size=(2, 4096))).cuda()
+    oa, ob = torch.zeros(1, dtype=torch.long).cuda(), torch.tensor([1, 0]).cuda()
+    kw = lambda s: dict(splice_donor_idx=torch.sort(torch.randint(0, s.shape[1], (s.shape[0], 5), device="cuda"))[0],
+                        splice_acceptor_idx=torch.sort(torch.randint(0, s.shape[1], (s.shape[0], 7), device="cuda"))[0])
+    ka, kb = kw(a), kw(b)
+    want_a = {k: v.clone() for k, v in model(a, oa, **ka)["mouse"].items()}
+    want_b = {k: v.clone() for k, v in model(b, ob, **kb)["mouse"].items()}
+    model.enable_cuda_graphs(True)
+    for _ in range(3):
+        for s, o, k, want in ((a, oa, ka, want_a), (b, ob, kb, want_b)):
+            got = model(s, o, **k)["mouse"]
+            torch.cuda.synchronize()
+            for name in want:
+                assert torch.equal(got[name], want[name]), name
+    assert len(eng._graphs) == 2
+    # a weight update through load_state_dict re-captures; invalidate() drops everything
+    eng.invalidate()
+    assert len(eng._graphs) == 0
 
 
 # ---------------------------------------------------------------------------------------------- sequence patterns
