@@ -106,6 +106,30 @@ class AgAttnArgs(C.Structure):
     ]
 
 
+class AgAffineArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("res", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("out_bf16", C.c_void_p),
+        ("x_bstride", C.c_int64),
+        ("shift_bstride", C.c_int64),
+        ("res_bstride", C.c_int64),
+        ("out_f32_bstride", C.c_int64),
+        ("out_bf16_bstride", C.c_int64),
+        ("x_ld", C.c_int32),
+        ("res_ld", C.c_int32),
+        ("out_f32_ld", C.c_int32),
+        ("out_bf16_ld", C.c_int32),
+        ("B", C.c_int32),
+        ("rows", C.c_int32),
+        ("C", C.c_int32),
+        ("act", C.c_int32),
+    ]
+
+
 ACT_NONE, ACT_GELU1702, ACT_GELU_ERF, ACT_RELU, ACT_SOFTPLUS_MUL, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
 
 # every symbol include/agb200.h declares; tests check the built library exports all of them
@@ -129,6 +153,9 @@ EXPORTED = [
     "ag_pair_out_embed_fwd",
     "ag_rmsnorm_act_fwd",
     "ag_splice_rope_fwd",
+    "ag_bn_stats_fwd",
+    "ag_bn_update_fwd",
+    "ag_affine_act_fwd",
 ]
 
 _lib = None
@@ -171,6 +198,9 @@ def load() -> C.CDLL:
     lib.ag_pair_out_embed_fwd.argtypes = [P] * 6 + [I32] * 4 + [C.c_int, P]
     lib.ag_rmsnorm_act_fwd.argtypes = [P] * 5 + [I64, I64, I32, I32, C.c_int, P]
     lib.ag_splice_rope_fwd.argtypes = [P] * 6 + [I32] * 6 + [C.c_int, P]
+    lib.ag_bn_stats_fwd.argtypes = [P, P, I32, I32, I64, I32, I32, C.c_int, P]
+    lib.ag_bn_update_fwd.argtypes = [P, C.c_double, P, P, C.c_float, C.c_float, P, P, P, P, I32, C.c_int, P]
+    lib.ag_affine_act_fwd.argtypes = [C.POINTER(AgAffineArgs), C.c_int, P]
     lib.ag_gemm_set_cta_group.argtypes = [C.c_int]
     lib.ag_gemm_set_cta_group.restype = C.c_int
     for name in EXPORTED[6:]:

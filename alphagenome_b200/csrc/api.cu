@@ -235,4 +235,24 @@ int ag_splice_rope_fwd(const float* x, const float* scale, const float* offset, 
                             static_cast<cudaStream_t>(stream));
 }
 
+int ag_bn_stats_fwd(const float* x, double* sums, int32_t B, int32_t rows, int64_t bstride, int32_t ld, int32_t C, int device,
+                    void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_bn_stats(x, sums, B, rows, bstride, ld, C, device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_bn_update_fwd(const double* sums, double count, float* running_var, const float* gamma, float momentum, float eps,
+                     float* scale_out, const float* fold_bias, const float* fold_beta, float* fold_shift_out, int32_t C,
+                     int device, void* stream) {
+  if (int rc = ensure_device(device)) return rc;
+  return launch_bn_update(sums, count, running_var, gamma, momentum, eps, scale_out, fold_bias, fold_beta, fold_shift_out, C,
+                          device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_affine_act_fwd(const AgAffineArgs* args, int device, void* stream) {
+  if (!args) return set_error("ag_affine_act_fwd: null args");
+  if (int rc = ensure_device(device)) return rc;
+  return launch_affine_act(*args, device, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

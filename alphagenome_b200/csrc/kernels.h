@@ -54,4 +54,10 @@ int launch_rmsnorm_act(const float* x, const float* w, const float* b, const flo
 int launch_splice_rope(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
                        void* out, int B, int P, int T, int Hd, int p_ld, int tab_per_site, int device, cudaStream_t st);
 
+int launch_bn_stats(const float* x, double* sums, int B, int rows, long bstride, int ld, int C, int device, cudaStream_t st);
+int launch_bn_update(const double* sums, double count, float* running_var, const float* gamma, float momentum, float eps,
+                     float* scale_out, const float* fold_bias, const float* fold_beta, float* fold_shift_out, int C, int device,
+                     cudaStream_t st);
+int launch_affine_act(const AgAffineArgs& a, int device, cudaStream_t st);
+
 }  // namespace agb

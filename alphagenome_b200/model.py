@@ -40,11 +40,15 @@ def geomspace(start: float, stop: float, num: int) -> torch.Tensor:
 
 # --------------------------------------------------------------------------------------------- parameter holders
 class BatchRMSNorm(nn.Module):
-    """AG:302-361. Inference uses the frozen running variance; the kernels fold it into a per-channel affine."""
+    """AG:302-361.  Frozen (update_running_var False, or None in eval mode): a per-channel affine folded into the
+    producing kernel's epilogue.  Updating (the reference's default, AG:331-340): the engine re-estimates running_var
+    from the batch in this buffer before normalising (ag_bn_stats_fwd / ag_bn_update_fwd / ag_affine_act_fwd)."""
 
     def __init__(self, dim_feat, channel_first=False, distributed=True, momentum=0.9, eps=1e-5, update_running_var=True):
         super().__init__()
         self.eps = eps
+        self.momentum = 1.0 - momentum      # AG:315: the lerp weight of the new batch variance
+        self.distributed = distributed
         self.channel_first = channel_first
         self.gamma = nn.Parameter(torch.ones(dim_feat))
         self.beta = nn.Parameter(torch.zeros(dim_feat))
@@ -298,7 +302,7 @@ class OutputPairEmbedding(nn.Module):
 
 
 def set_update_running_var(root: nn.Module, update_running_var):
-    """AG:365-371 (kept for API compatibility; the B200 forward is inference-only and never updates statistics)."""
+    """AG:365-371."""
     for mod in root.modules():
         if isinstance(mod, BatchRMSNorm):
             mod.update_running_var = update_running_var

@@ -396,3 +396,64 @@ def splice_rope(x, scale, offset, cos_tab, sin_tab, out) -> None:
     _require(out.dtype == torch.bfloat16 and out.is_contiguous() and out.dim() == 4 and out.shape[0] == B and out.shape[1] == T and out.shape[2] >= P and out.shape[3] == Hd, "out must be bf16 [B, T, >=P, H]")
     _lib.check(_lib.load().ag_splice_rope_fwd(x.data_ptr(), scale.data_ptr(), offset.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), out.data_ptr(),
                                               B, P, T, Hd, out.shape[2], 1 if per_site else 0, _dev(x), _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ updating BatchRMSNorm
+def bn_stats(x: torch.Tensor, sums: torch.Tensor) -> None:
+    """ag_bn_stats_fwd: x fp32 [B, rows, C] view (last dim contiguous) -> sums fp64 [2, C] (sum, sum of squares)."""
+    x = _as3(x)
+    _require(x.is_cuda and x.dtype == torch.float32, "x must be a CUDA fp32 tensor")
+    B, rows, Cc = x.shape
+    _require(sums.dtype == torch.float64 and sums.is_contiguous() and tuple(sums.shape) == (2, Cc), "sums must be fp64 [2, C]")
+    bs = x.stride(0) if B > 1 else x.stride(1) * rows
+    _lib.check(_lib.load().ag_bn_stats_fwd(x.data_ptr(), sums.data_ptr(), B, rows, bs, x.stride(1), Cc, _dev(x), _stream()))
+
+
+def bn_update(sums, count: float, running_var, gamma, momentum: float, eps: float, scale_out, fold_bias=None, fold_beta=None,
+              fold_shift_out=None) -> None:
+    """ag_bn_update_fwd: running_var.lerp_(batch variance, momentum) in place; scale_out = gamma / sqrt(running_var + eps)."""
+    Cc = running_var.numel()
+    for t, nm in ((running_var, "running_var"), (gamma, "gamma"), (scale_out, "scale_out"), (fold_bias, "fold_bias"), (fold_beta, "fold_beta"),
+                  (fold_shift_out, "fold_shift_out")):
+        _f32(t, nm)
+        _require(t is None or t.numel() == Cc, f"{nm} must have C elements")
+    _require(sums.dtype == torch.float64 and sums.is_contiguous() and sums.numel() == 2 * Cc, "sums must be fp64 [2, C]")
+    _lib.check(_lib.load().ag_bn_update_fwd(sums.data_ptr(), float(count), running_var.data_ptr(), gamma.data_ptr(), float(momentum), float(eps),
+                                            scale_out.data_ptr(), _ptr(fold_bias), _ptr(fold_beta), _ptr(fold_shift_out), Cc, _dev(running_var), _stream()))
+
+
+def affine_act(x, scale=None, shift=None, *, res=None, out_f32=None, out_bf16=None, act: int = ACT_NONE) -> None:
+    """ag_affine_act_fwd: y = x * scale[c] + shift[(b,) c] (+ res); out_f32 / out_bf16 = act(y).  [B, rows, C] views."""
+    x = _as3(x)
+    B, rows, Cc = x.shape
+    _require(x.is_cuda and x.dtype == torch.float32, "x must be a CUDA fp32 tensor")
+
+    def bst(t):
+        return t.stride(0) if B > 1 else t.stride(1) * rows
+
+    a = _lib.AgAffineArgs()
+    a.x, a.x_bstride, a.x_ld = x.data_ptr(), bst(x), x.stride(1)
+    _f32(scale, "scale")
+    a.scale = _ptr(scale)
+    a.shift_bstride = 0
+    if shift is not None:
+        _f32(shift, "shift")
+        _require(shift.shape[-1] == Cc, "shift must be [C] or [B, C]")
+        if shift.dim() == 2:
+            _require(shift.shape[0] == B, "shift batch mismatch")
+            a.shift_bstride = Cc
+    a.shift = _ptr(shift)
+    if res is not None:
+        r = _as3(res)
+        _require(r.dtype == torch.float32 and tuple(r.shape) == (B, rows, Cc), "res must be fp32 with x's shape")
+        a.res, a.res_bstride, a.res_ld = r.data_ptr(), bst(r), r.stride(1)
+    if out_f32 is not None:
+        o = _as3(out_f32)
+        _require(o.dtype == torch.float32 and tuple(o.shape) == (B, rows, Cc), "out_f32 must be fp32 with x's shape")
+        a.out_f32, a.out_f32_bstride, a.out_f32_ld = o.data_ptr(), bst(o), o.stride(1)
+    if out_bf16 is not None:
+        o = _as3(out_bf16)
+        _require(o.dtype == torch.bfloat16 and tuple(o.shape) == (B, rows, Cc), "out_bf16 must be bf16 with x's shape")
+        a.out_bf16, a.out_bf16_bstride, a.out_bf16_ld = o.data_ptr(), bst(o), o.stride(1)
+    a.B, a.rows, a.C, a.act = B, rows, Cc, int(act)
+    _lib.check(_lib.load().ag_affine_act_fwd(C.byref(a), _dev(x), _stream()))

@@ -42,6 +42,21 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+class _Norm:
+    """One packed BatchRMSNorm (AG:302-361): `s` = gamma / sqrt(running_var + eps) and `t` = beta are the vectors the
+    fused kernels read; `mod` is the module whose running_var an updating forward re-estimates in place."""
+
+    __slots__ = ("mod", "s", "t", "fold_bias", "fold_shift")
+
+    def __init__(self, mod, s, t):
+        self.mod, self.s, self.t = mod, s, t
+        self.fold_bias = self.fold_shift = None   # sandwich post-norms: shift = bias * s + t folded behind the Linear
+
+    def updating(self) -> bool:
+        u = getattr(self.mod, "update_running_var", None)       # default(arg, self.update_running_var, self.training), AG:331
+        return bool(self.mod.training if u is None else u)
+
+
 class TrunkEngine:
     def __init__(self, unet):
         self.unet = weakref.ref(unet)
@@ -49,6 +64,8 @@ class TrunkEngine:
         self._pack: Optional[Dict] = None
         self._pack_key = None
         self._tensors = None   # (model, [parameters and buffers]) the version key walks
+        self._norms: Dict = {}  # data_ptr of a packed scale vector -> _Norm
+        self._own = None       # (first owned bp, end, window bp) of a sequence-parallel conv window
         self._rope: Dict = {}
         self._rel: Dict = {}
         self.collect = None  # optional callback(name, tensor) for per-stage parity tests
@@ -71,18 +88,24 @@ class TrunkEngine:
         if self._pack is not None and self._pack_key == key:
             return self._pack
         unet = self.unet()
-        if not getattr(self, "_warned_frozen", False):
-            # The reference's BatchRMSNorm re-estimates running_var from the batch on EVERY forward unless it is frozen
-            # (update_running_var defaults to True, AG:331; its inference tests call set_update_running_var(model, False)).
-            # The B200 forward always normalises with the stored running_var and never modifies it.
-            mods = [unet] + ([self.model()] if self.model is not None and self.model() is not None else [])
-            if any(getattr(m, "update_running_var", False) for root in mods for m in root.modules() if type(m).__name__ == "BatchRMSNorm"):
-                import warnings
-
-                warnings.warn("alphagenome_b200 runs BatchRMSNorm with frozen statistics (the stored running_var is used and "
-                              "never updated); call set_update_running_var(model, False) on the reference model for identical behaviour",
-                              stacklevel=3)
-            self._warned_frozen = True
+        tw0 = unet.transformer
+        at0 = tw0.layers[0][0].block
+        s2p0 = next((lyr[2] for lyr in tw0.layers if lyr[2] is not None), None)
+        bad = []
+        if getattr(tw0, "polar_pos_emb", False) or getattr(tw0, "rotary_emb", None) is None:
+            bad.append("polar_pos_emb=True (PoPE)")
+        if not hasattr(at0.q_norm, "bias") or at0.q_norm.bias is None:
+            bad.append("use_qk_rmsnorm=True")
+        if at0.to_attn_bias[2].weight.shape != (8, 128):
+            bad.append(f"attention heads / pair dim {tuple(at0.to_attn_bias[2].weight.shape)} (kernels are built for 8 heads x 128)")
+        if at0.q_norm.weight.numel() != 128 or at0.v_norm.weight.numel() != 192:
+            bad.append("dim_head_qk / dim_head_v other than 128 / 192")
+        if at0.to_qkv.weight.shape[0] != 8 * 128 + 128 + 192:
+            bad.append("kv_heads > 1")
+        if s2p0 is not None and (getattr(s2p0, "pool_size", 16) != 16 or s2p0.qk_to_pairwise.weight.shape != (128, 32)):
+            bad.append("SingleToPairwise pool_size / heads / dim_pairwise other than 16 / 32 / 128")
+        if bad:
+            raise ops._lib.AgbError("alphagenome_b200 implements the default trunk configuration only; unsupported: " + "; ".join(bad))
         if device.type != "cuda" and not getattr(self, "_allow_cpu_pack", False):  # (tests pack on CPU to compare layouts)
             raise ops._lib.AgbError("alphagenome_b200 runs only on a CUDA (sm_100a) device; move the model and inputs to cuda")
         f32 = dict(device=device, dtype=torch.float32)
@@ -96,9 +119,17 @@ class TrunkEngine:
         def wlin(lin):  # [N, K] -> bf16 [1, N, K]
             return lin.weight.detach().to(device).to(torch.bfloat16).contiguous().unsqueeze(0)
 
-        def aff(norm):
+        self._norms = {}
+
+        def aff(norm, s_into=None, t_into=None):
             s, t = norm.affine()
-            return vec(s), vec(t)
+            s, t = vec(s), vec(t)
+            if s_into is not None:      # a row of a stacked parameter set the kernel reads as one tensor
+                s_into.copy_(s)
+                t_into.copy_(t)
+                s, t = s_into, t_into
+            self._norms[s.data_ptr()] = _Norm(norm, s, t)
+            return s, t
 
         def convblock(cb):
             s, t = aff(cb.norm)
@@ -118,23 +149,43 @@ class TrunkEngine:
                          scale=vec(u.residual_scale)) for u in unet.ups]
 
         tw = unet.transformer
+        # to_attn_bias of a pair-updating layer and of the following layer that reuses the same pair tensor are projected
+        # in one pass over it (ag_pair_bias_fwd takes up to two parameter sets): their (scale, shift, W) live stacked
+        has_pair = [lyr[2] is not None for lyr in tw.layers]
+        groups = []
+        for li in range(len(tw.layers)):
+            if has_pair[li] or li == 0:
+                groups.append([li] + ([li + 1] if li + 1 < len(tw.layers) and not has_pair[li + 1] else []))
+            elif not any(li in g for g in groups):
+                groups.append([li])
+        bias_slot = {li: (gi, k) for gi, g in enumerate(groups) for k, li in enumerate(g)}
+        at0 = tw.layers[0][0].block
+        Hb, Cp = at0.to_attn_bias[2].weight.shape
+        bias_sets = [dict(layers=g, s=torch.empty(len(g), Cp, **f32), t=torch.empty(len(g), Cp, **f32), W=torch.empty(len(g), Hb, Cp, **f32))
+                     for g in groups]
         layers = []
-        for attn_w, ff_w, s2p, pattn_w, pff_w in tw.layers:
+        for li, (attn_w, ff_w, s2p, pattn_w, pff_w) in enumerate(tw.layers):
             L: Dict = {}
             at = attn_w.block
             s_pre, t_pre = aff(attn_w.pre_rmsnorm)
             s_post, t_post = aff(attn_w.post_rmsnorm)
-            ab_s, ab_t = aff(at.to_attn_bias[0])
+            gi, gk = bias_slot[li]
+            ab_s, ab_t = aff(at.to_attn_bias[0], bias_sets[gi]["s"][gk], bias_sets[gi]["t"][gk])
+            bias_sets[gi]["W"][gk].copy_(vec(at.to_attn_bias[2].weight))
+            nrm = self._norms[s_post.data_ptr()]
+            nrm.fold_bias, nrm.fold_shift = vec(at.to_out.bias), (vec(at.to_out.bias) * s_post + t_post).contiguous()
             L["attn"] = dict(
                 pre=(s_pre, t_pre), Wqkv=wlin(at.to_qkv), Wout=wlin(at.to_out),
-                out_scale=s_post.clone(), out_shift=(vec(at.to_out.bias) * s_post + t_post).contiguous(),
+                out_scale=s_post, out_shift=nrm.fold_shift,
                 qw=vec(at.q_norm.weight), qb=vec(at.q_norm.bias), kw=vec(at.k_norm.weight), kb=vec(at.k_norm.bias),
-                vw=vec(at.v_norm.weight), vb=vec(at.v_norm.bias), ab_s=ab_s, ab_t=ab_t, ab_W=vec(at.to_attn_bias[2].weight),
+                vw=vec(at.v_norm.weight), vb=vec(at.v_norm.bias), ab_s=ab_s, ab_t=ab_t, ab_W=bias_sets[gi]["W"][gk],
                 heads=at.heads, d=at.dim_head_qk, dv=at.dim_head_v, scale=at.scale, softcap=at.softclamp_value)
             fs_pre, ft_pre = aff(ff_w.pre_rmsnorm)
             fs_post, ft_post = aff(ff_w.post_rmsnorm)
+            nrm = self._norms[fs_post.data_ptr()]
+            nrm.fold_bias, nrm.fold_shift = vec(ff_w.block[3].bias), (vec(ff_w.block[3].bias) * fs_post + ft_post).contiguous()
             L["ff"] = dict(pre=(fs_pre, ft_pre), W1=wlin(ff_w.block[0]), b1=vec(ff_w.block[0].bias), W2=wlin(ff_w.block[3]),
-                           out_scale=fs_post.clone(), out_shift=(vec(ff_w.block[3].bias) * fs_post + ft_post).contiguous())
+                           out_scale=fs_post, out_shift=nrm.fold_shift)
             if s2p is not None:
                 H, dp = s2p.heads, s2p.dim_pairwise
                 L["s2p"] = dict(
@@ -147,17 +198,9 @@ class TrunkEngine:
                 L["pff"] = dict(nw=vec(pff_w.pre_rmsnorm.weight), nb=vec(pff_w.pre_rmsnorm.bias), W1=wlin(pff_w.block[0]),
                                 b1=vec(pff_w.block[0].bias), W2=wlin(pff_w.block[3]), b2=vec(pff_w.block[3].bias))
             layers.append(L)
-        # to_attn_bias of a pair-updating layer and of the following layer(s) that reuse the same pair tensor are
-        # projected in one pass over it (ag_pair_bias_fwd takes up to two parameter sets)
-        for li, L in enumerate(layers):
-            if "s2p" in L or li == 0:
-                grp = [li]
-                if li + 1 < len(layers) and "s2p" not in layers[li + 1]:
-                    grp.append(li + 1)
-                ats = [layers[j]["attn"] for j in grp]
-                L["bias_group"] = dict(layers=grp, s=torch.stack([a["ab_s"] for a in ats]).contiguous(),
-                                       t=torch.stack([a["ab_t"] for a in ats]).contiguous(),
-                                       W=torch.stack([a["ab_W"] for a in ats]).contiguous())
+        for g in bias_sets:
+            if len(g["layers"]) == 2 or "s2p" in layers[g["layers"][0]] or g["layers"][0] == 0:
+                layers[g["layers"][0]]["bias_group"] = g
         P["layers"] = layers
         P["inv_freq"] = tw.rotary_emb.inv_freq.detach().float().cpu()
 
@@ -199,6 +242,97 @@ class TrunkEngine:
             self._rel[key] = R[0]
         return self._rel[key]
 
+    # ------------------------------------------------------------------------------------------ updating BatchRMSNorm
+    def _updating(self, scale) -> Optional[_Norm]:
+        """The packed norm behind `scale` if its module re-estimates running_var on this forward (AG:331), else None."""
+        if scale is None:
+            return None
+        nrm = self._norms.get(scale.data_ptr())
+        return nrm if nrm is not None and nrm.updating() else None
+
+    def _own_rows(self, x):
+        """Rows of a conv-stack tensor this rank owns (statistics exclude the recomputed halo rows of a shard)."""
+        if self._own is None:
+            return x
+        lo, hi, win = self._own
+        f = win // x.shape[1]
+        return x[:, lo // f: hi // f]
+
+    def _bn_update(self, nrm: _Norm, src):
+        """running_var.lerp_(var(src), momentum) in the module's buffer and the packed scale (AG:331-340): one pass of
+        per-channel sums over this rank's rows, ONE all-reduce under sequence parallelism (the reference: three)."""
+        rv = nrm.mod.running_var
+        if rv.device != src.device or rv.dtype != torch.float32 or not rv.is_contiguous():
+            raise ops._lib.AgbError("updating BatchRMSNorm needs the module's fp32 running_var on the forward's device")
+        src = self._own_rows(src)
+        B, rows, Cc = src.shape
+        sums = torch.empty(2, Cc, device=src.device, dtype=torch.float64)
+        ops.bn_stats(src, sums)
+        count = B * rows
+        if self.sp is not None and self.sp.world > 1 and getattr(nrm.mod, "distributed", True):
+            sums = self.sp.all_reduce_sum(sums)
+            count *= self.sp.world
+        gamma = nrm.mod.gamma.detach()
+        if gamma.device != src.device or gamma.dtype != torch.float32:
+            gamma = gamma.to(device=src.device, dtype=torch.float32)
+        ops.bn_update(sums, count, rv, gamma.contiguous(), getattr(nrm.mod, "momentum", 0.1), nrm.mod.eps, nrm.s,
+                      fold_bias=nrm.fold_bias, fold_beta=nrm.t if nrm.fold_shift is not None else None, fold_shift_out=nrm.fold_shift)
+
+    def _gemm(self, A, W, **kw):
+        """ops.gemm, except that activated outputs whose BatchRMSNorm re-estimates its variance are produced after the
+        GEMM: the fp32 value is written first, its per-channel statistics update the norm, then the output is made."""
+        deferred = [(k, kw[k]) for k in ("actA", "actB", "actP") if kw.get(k) is not None and self._updating(kw[k].scale) is not None]
+        if not deferred:
+            return ops.gemm(A, W, **kw)
+        for k, _ in deferred:
+            kw[k] = None
+        Arows = A.shape[-2] if kw.get("M") is None else kw["M"]
+        for slot, keys in (("out", ("actA", "actB")), ("pool", ("actP",))):
+            acts = [a for k, a in deferred if k in keys]
+            if not acts:
+                continue
+            src = kw.get(slot)
+            if src is None:     # an fp32 destination of the same norm doubles as the raw buffer (normalised in place)
+                f32_dst = [a.dst for a in acts if a.dst.dtype == torch.float32]
+                src = f32_dst[0] if f32_dst else torch.empty(acts[0].dst.shape, device=A.device, dtype=torch.float32)
+                kw[slot] = src
+        ops.gemm(A, W, **kw)
+        done = set()
+        for slot, keys in (("out", ("actA", "actB")), ("pool", ("actP",))):
+            acts = [a for k, a in deferred if k in keys]
+            src = kw.get(slot)
+            acts.sort(key=lambda a: a.dst.data_ptr() == src.data_ptr())   # the destination that aliases the raw buffer goes last
+            for a in acts:
+                nrm = self._norms[a.scale.data_ptr()]
+                if id(nrm) not in done:
+                    self._bn_update(nrm, src)
+                    done.add(id(nrm))
+                ops.affine_act(src, a.scale, a.shift, out_f32=a.dst if a.dst.dtype == torch.float32 else None,
+                               out_bf16=a.dst if a.dst.dtype == torch.bfloat16 else None, act=a.act)
+
+    def _post_norm_gemm(self, A, W, blk, single, act: Optional[Act], actB: Optional[Act] = None):
+        """Sandwich block tail (AG:630-639, 1024-1025): single += post_norm(A @ W^T + bias), then the next block's
+        pre-normalised operand(s).  Frozen: one GEMM with the norm folded into its epilogue."""
+        post = self._updating(blk["out_scale"])
+        if post is None and (act is None or self._updating(act.scale) is None):
+            ops.gemm(A, W, pre_scale=blk["out_scale"], pre_shift=blk["out_shift"], res=single, out=single, actA=act, actB=actB)
+            return
+        if post is not None:
+            raw = torch.empty_like(single)
+            ops.gemm(A, W, pre_shift=post.fold_bias, out=raw)
+            self._bn_update(post, raw)
+            ops.affine_act(raw, post.s, post.t, res=single, out_f32=single)
+        else:
+            ops.gemm(A, W, pre_scale=blk["out_scale"], pre_shift=blk["out_shift"], res=single, out=single)
+        for a in (act, actB):
+            if a is None:
+                continue
+            nrm = self._updating(a.scale)
+            if nrm is not None:
+                self._bn_update(nrm, single)
+            ops.affine_act(single, a.scale, a.shift, out_f32=a.dst if a.dst.dtype == torch.float32 else None,
+                           out_bf16=a.dst if a.dst.dtype == torch.bfloat16 else None, act=a.act)
+
     # ------------------------------------------------------------------------------------------ forward pieces
     def _note(self, name, t):
         if self.collect is not None:
@@ -220,7 +354,7 @@ class TrunkEngine:
         pw = P["pointwise"]
         x0 = torch.empty(B, L, C0, **f32)
         a0 = torch.empty(B, L, C0, **bf)
-        ops.gemm(X, e["W"], pre_shift=e["b"], out=x0, actA=Act(a0, pw["s"], pw["t"], ACT_GELU1702))
+        self._gemm(X, e["W"], pre_shift=e["b"], out=x0, actA=Act(a0, pw["s"], pw["t"], ACT_GELU1702))
         del X
         ups = P["ups"]
         skips = [None] * (n_down + 1)  # skips[j] feeds ups[j]
@@ -229,7 +363,7 @@ class TrunkEngine:
         x = torch.empty(B, L // 2, C0, **f32)
         a = torch.empty(B, L // 2, C0, **bf)
         d0 = P["downs"][0]["conv"]
-        ops.gemm(a0, pw["W"], pre_shift=pw["b"], res=x0, actA=Act(skips[n_down], un["s"], un["t"], ACT_GELU1702),
+        self._gemm(a0, pw["W"], pre_shift=pw["b"], res=x0, actA=Act(skips[n_down], un["s"], un["t"], ACT_GELU1702),
                  pool=x, actP=Act(a, d0["s"], d0["t"], ACT_GELU1702))
         del x0, a0
         self._note("embed.pooled", x)
@@ -239,7 +373,7 @@ class TrunkEngine:
             C_in, C_out = c["W"].shape[2], c["W"].shape[1]
             y1 = torch.empty(B, length, C_out, **f32)
             ay1 = torch.empty(B, length, C_out, **bf)
-            ops.gemm(a, c["W"], pre_shift=c["b"], res=x, res_ch=C_in, out=y1, actA=Act(ay1, co["s"], co["t"], ACT_GELU1702))
+            self._gemm(a, c["W"], pre_shift=c["b"], res=x, res_ch=C_in, out=y1, actA=Act(ay1, co["s"], co["t"], ACT_GELU1702))
             j = n_down - 1 - i
             un = ups[j]["unet_conv"]
             skips[j] = torch.empty(B, length, C_out, **bf)
@@ -250,7 +384,7 @@ class TrunkEngine:
                 nx = P["downs"][i + 1]["conv"]
                 an = torch.empty(B, length // 2, C_out, **bf)
                 actP = Act(an, nx["s"], nx["t"], ACT_GELU1702)
-            ops.gemm(ay1, co["W"], pre_shift=co["b"], res=y1, actA=Act(skips[j], un["s"], un["t"], ACT_GELU1702), pool=xn, actP=actP)
+            self._gemm(ay1, co["W"], pre_shift=co["b"], res=y1, actA=Act(skips[j], un["s"], un["t"], ACT_GELU1702), pool=xn, actP=actP)
             x, a = xn, an
             length //= 2
             self._note(f"downs.{i}.pooled", x)
@@ -339,6 +473,10 @@ class TrunkEngine:
         if org_embed is None:
             org_embed = torch.zeros(B, D, **f32)
         ops.add_embed_norm(x, org_embed.to(torch.float32).contiguous(), s0, t0, single, a)
+        nrm0 = self._updating(s0)
+        if nrm0 is not None:     # the first pre-norm sees x + organism embedding (AG:1119-1120, 636)
+            self._bn_update(nrm0, single)
+            ops.affine_act(single, s0, t0, out_bf16=a)
         cos_t, sin_t = self.rope_tables(n, dev, offset=plan.tok_off if sharded else 0)
         pair = None
         bias_of = {}
@@ -360,6 +498,12 @@ class TrunkEngine:
             nk = _round_up(n_all, 8)
             Vt = torch.empty(B, dv, nk, **bf)
             ops.transpose_bf16(V, Vt)
+            if "bias_group" in L or li not in bias_of:
+                # to_attn_bias' BatchRMSNorm (AG:688-693) of the layer(s) projected in this pass
+                for j in (L["bias_group"]["layers"] if "bias_group" in L else [li]):
+                    nrm = self._updating(layers[j]["attn"]["ab_s"])
+                    if nrm is not None:
+                        self._bn_update(nrm, pair.view(B, -1, pair.shape[-1]))
             if "bias_group" in L:
                 bg = L["bias_group"]
                 bias_sets = torch.empty(len(bg["layers"]), B, Hh, pair.shape[1], pair.shape[2], **f32)
@@ -376,18 +520,15 @@ class TrunkEngine:
             ops.attention(Q.view(B, n, Hh, d).permute(0, 2, 1, 3), K.unsqueeze(1), Vt.view(B, 1, dv, nk),
                           O.view(B, n, Hh, dv).permute(0, 2, 1, 3), mode=0, scale=at["scale"], bias=bias, softcap=at["softcap"])
             ff = L["ff"]
-            ops.gemm(O, at["Wout"], pre_scale=at["out_scale"], pre_shift=at["out_shift"], res=single, out=single,
-                     actA=Act(a_ff, ff["pre"][0], ff["pre"][1]))
+            self._post_norm_gemm(O, at["Wout"], at, single, Act(a_ff, ff["pre"][0], ff["pre"][1]))
             hid = torch.empty(B, n, ff["W1"].shape[1], **bf)
             ops.gemm(a_ff, ff["W1"], pre_shift=ff["b1"], relu=True, actA=Act(hid))
             last = li + 1 == len(layers)
             if not last:
                 nxt = layers[li + 1]["attn"]["pre"]
-                ops.gemm(hid, ff["W2"], pre_scale=ff["out_scale"], pre_shift=ff["out_shift"], res=single, out=single,
-                         actA=Act(a, nxt[0], nxt[1]))
+                self._post_norm_gemm(hid, ff["W2"], ff, single, Act(a, nxt[0], nxt[1]))
             else:
-                ops.gemm(hid, ff["W2"], pre_scale=ff["out_scale"], pre_shift=ff["out_shift"], res=single, out=single,
-                         actA=final_act, actB=Act(final_plain) if final_plain is not None else None)
+                self._post_norm_gemm(hid, ff["W2"], ff, single, final_act, Act(final_plain) if final_plain is not None else None)
             self._note(f"tower.layer{li}.single", single)
             self._note(f"tower.layer{li}.pair", pair)
         return single, pair
@@ -403,21 +544,21 @@ class TrunkEngine:
             c, un, co = u["conv"], u["unet_conv"], u["conv_out"]
             C_out = c["W"].shape[1]
             low = torch.empty(B, length, C_out, **f32)
-            ops.gemm(a, c["W"], pre_shift=c["b"], res=x, res_ch=C_out, post_scale=u["scale"], out=low)
+            self._gemm(a, c["W"], pre_shift=c["b"], res=x, res_ch=C_out, post_scale=u["scale"], out=low)
             y = torch.empty(B, 2 * length, C_out, **f32)
             ay = torch.empty(B, 2 * length, C_out, **bf)
-            ops.gemm(skips[j], un["W"], pre_shift=un["b"], res=low, res_shift=1, out=y, actA=Act(ay, co["s"], co["t"], ACT_GELU1702))
+            self._gemm(skips[j], un["W"], pre_shift=un["b"], res=low, res_shift=1, out=y, actA=Act(ay, co["s"], co["t"], ACT_GELU1702))
             skips[j] = None
             xn = torch.empty(B, 2 * length, C_out, **f32)
             if j + 1 < len(ups):
                 nx = ups[j + 1]["conv"]
                 an = torch.empty(B, 2 * length, C_out, **bf)
-                ops.gemm(ay, co["W"], pre_shift=co["b"], res=y, out=xn, actA=Act(an, nx["s"], nx["t"], ACT_GELU1702))
+                self._gemm(ay, co["W"], pre_shift=co["b"], res=y, out=xn, actA=Act(an, nx["s"], nx["t"], ACT_GELU1702))
             else:
                 an = None
                 if want_plain:
                     plain = torch.empty(B, 2 * length, C_out, **bf)
-                ops.gemm(ay, co["W"], pre_shift=co["b"], res=y, out=xn, actA=Act(plain) if want_plain else None)
+                self._gemm(ay, co["W"], pre_shift=co["b"], res=y, out=xn, actA=Act(plain) if want_plain else None)
             x, a = xn, an
             length *= 2
             self._note(f"ups.{j}", x)
@@ -438,7 +579,9 @@ class TrunkEngine:
         if sharded:
             seq = seq[:, plan.win_start:plan.win_end]
         seq = seq.to(torch.int64).contiguous()
+        self._own = (plan.halo_left, plan.halo_left + plan.L_loc, seq.shape[1]) if sharded else None
         x, skips = self._encoder(P, seq)
+        self._own = None
         hl, hr = (plan.halo_tok_left, plan.halo_tok_right) if sharded else (0, 0)
         if sharded:
             x = x[:, hl:hl + plan.n_loc].contiguous()  # the halo tokens only existed to make the owned ones exact
@@ -455,7 +598,9 @@ class TrunkEngine:
             (l32, r32), (l16, r16) = self.sp.exchange_halos([single, a_dec], ht)   # one collective for both
             x_dec = torch.cat([t for t in (l32, single, r32) if t is not None], dim=1)
             a_dec = torch.cat([t for t in (l16, a_dec, r16) if t is not None], dim=1)
+        self._own = (plan.halo_left, plan.halo_left + plan.L_loc, seq.shape[1]) if sharded else None
         unet_out, unet_b16 = self._decoder(P, x_dec, a_dec, skips, want_plain=with_embeds)
+        self._own = None
         if sharded:
             unet_out = unet_out[:, plan.halo_left:plan.halo_left + plan.L_loc]
             if unet_b16 is not None:
@@ -467,7 +612,7 @@ class TrunkEngine:
             t128 = o128["table"].index_select(0, organism_index)
             e128 = torch.empty(B, n, o128["W"].shape[1], **f32)
             e128_b16 = torch.empty(B, n, o128["W"].shape[1], **bf)
-            ops.gemm(single_b16, o128["W"], pre_shift=o128["b"], actA=Act(e128, o128["s"], t128, ACT_GELU1702),
+            self._gemm(single_b16, o128["W"], pre_shift=o128["b"], actA=Act(e128, o128["s"], t128, ACT_GELU1702),
                      actB=Act(e128_b16, o128["s"], t128, ACT_GELU1702))
             skp = torch.empty(B, n, o1["Wskip"].shape[1], **f32)
             ops.gemm(e128_b16, o1["Wskip"], out=skp)
@@ -478,7 +623,7 @@ class TrunkEngine:
             e1 = torch.empty(B, Lfull, o1["W"].shape[1], **f32)
             # prediction heads take embeds_1bp as a bf16 MMA operand: emitted by the same epilogue when asked for
             e1_b16 = torch.empty(B, Lfull, o1["W"].shape[1], **bf) if want_head_operands else None
-            ops.gemm(unet_b16, o1["W"], pre_shift=o1["b"], res=skp, res_shift=shift, actA=Act(e1, o1["s"], t1, ACT_GELU1702),
+            self._gemm(unet_b16, o1["W"], pre_shift=o1["b"], res=skp, res_shift=shift, actA=Act(e1, o1["s"], t1, ACT_GELU1702),
                      actB=Act(e1_b16, o1["s"], t1, ACT_GELU1702) if want_head_operands else None)
             epair = torch.empty_like(pair)
             pairT = self.sp.transpose_blocks(pair) if sharded else None  # symmetrize needs pair[j, i] (AG:1253)

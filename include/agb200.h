@@ -211,6 +211,38 @@ int ag_add_embed_norm_fwd(const float* x, const float* emb, const float* scale, 
 int ag_pair_out_embed_fwd(const float* pair, const float* pairT, const float* w, const float* b, const float* emb,
                           float* out, int32_t B, int32_t rows, int32_t P, int32_t C, int device, void* stream);
 
+/* --- BatchRMSNorm with updating statistics (AG:324-361 with update_running_var, the reference's default; ---------
+ * --- get_maybe_dist_var AG:276-300).  The frozen path is folded into ag_gemm_fwd's epilogue instead. ---------- */
+
+/* sums[0..C) = sum over (b, row) of x[b][row][c];  sums[C..2C) = sum of squares; fp64, overwritten.  x fp32
+ * [B][rows][C] with row stride ld and batch stride bstride (elements); C a multiple of 128.  A sequence-parallel rank
+ * adds the other ranks' sums with ONE all-reduce (the reference uses three, AG:289-298). */
+int ag_bn_stats_fwd(const float* x, double* sums, int32_t B, int32_t rows, int64_t bstride, int32_t ld, int32_t C,
+                    int device, void* stream);
+
+/* var[c] = sums[C+c]/count - (sums[c]/count)^2 (population variance, AG:284);  running_var.lerp_(var, momentum) IN
+ * PLACE (AG:340; momentum = 1 - the constructor's momentum argument = 0.1);  scale_out[c] = gamma[c] /
+ * sqrt(running_var[c] + eps) (AG:344-359).  If fold_shift_out is non-null it also receives fold_bias[c] * scale + fold_beta[c]
+ * (the sandwich post-norm folded behind a Linear's bias, as ag_gemm_fwd's pre_scale / pre_shift use it). */
+int ag_bn_update_fwd(const double* sums, double count, float* running_var, const float* gamma, float momentum, float eps,
+                     float* scale_out, const float* fold_bias, const float* fold_beta, float* fold_shift_out, int32_t C,
+                     int device, void* stream);
+
+/* y = x * scale[c] + shift[b][c] (+ res);  out_f32 = act(y) and / or out_bf16 = act(y).  All tensors [B][rows][C]
+ * with their own row / batch strides (elements, multiples of 4).  act: NONE / GELU1702 / GELU_ERF / RELU. */
+typedef struct AgAffineArgs {
+  const float* x;
+  const float* scale;      /* [C] or NULL (= 1) */
+  const float* shift;      /* [C] (+ b*shift_bstride) or NULL (= 0) */
+  const float* res;        /* NULL = none */
+  float* out_f32;          /* NULL = disabled */
+  void* out_bf16;          /* NULL = disabled */
+  int64_t x_bstride, shift_bstride, res_bstride, out_f32_bstride, out_bf16_bstride;
+  int32_t x_ld, res_ld, out_f32_ld, out_bf16_ld;
+  int32_t B, rows, C, act;
+} AgAffineArgs;
+int ag_affine_act_fwd(const AgAffineArgs* args, int device, void* stream);
+
 /* --- prediction heads; their contractions run on ag_gemm_fwd ---------------------------- */
 
 /* ContactMapHead AG:1292-1298 after symmetrize (embeds_pair is already symmetric): RMSNormWithBias over the last dim,
