@@ -190,7 +190,7 @@ class Workload:
 
     def __init__(self, name, dev, sp=None, graphs=True):
         from alphagenome_b200.init_weights import apply_synth_weights
-        from alphagenome_b200.model import AlphaGenome, publication_heads_config
+        from alphagenome_b200.model import AlphaGenome, publication_heads_config, set_update_running_var
         from alphagenome_b200.trunk import engine_for
 
         w = WORKLOADS[name]
@@ -200,6 +200,7 @@ class Workload:
             for organism in ("human", "mouse"):
                 model.add_heads(**publication_heads_config[organism])
         self.model = model.to(dev).eval()
+        set_update_running_var(self.model, False)   # inference: frozen BatchRMSNorm statistics, as the reference's inference tests run it
         apply_synth_weights(self.model, seed=0)
         self.eng = engine_for(self.model.transformer_unet, self.model)
         self.eng.sp = sp
@@ -292,9 +293,10 @@ def secondary_workload(name, dev, world, steps, warmup, with_e2e=False):
 def parity_vs_oracle(dev, ref):
     """The B200 forward on the CPU arm's sample (same weights, same tokens) against the oracle outputs `ref`."""
     from alphagenome_b200.init_weights import apply_synth_weights
-    from alphagenome_b200.model import AlphaGenome
+    from alphagenome_b200.model import AlphaGenome, set_update_running_var
 
     model = AlphaGenome().to(dev).eval()
+    set_update_running_var(model, False)
     apply_synth_weights(model, seed=0)
     emb = model(synth_tokens(1, CPU_SAMPLE_L).to(dev), torch.zeros(1, dtype=torch.long, device=dev))
     torch.cuda.synchronize()

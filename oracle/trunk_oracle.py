@@ -36,7 +36,16 @@ def batch_rms_affine(sd: SD, p: str):
     return sd[p + "gamma"] / torch.sqrt(sd[p + "running_var"] + EPS), sd[p + "beta"]
 
 
+UPDATE_KEY = "__update_running_var__"   # sd[UPDATE_KEY] = True: BatchRMSNorm re-estimates running_var (the reference's default)
+
+
 def batch_rms(sd: SD, p: str, x):
+    """BatchRMSNorm.forward AG:324-361.  With sd[UPDATE_KEY] set, the population variance of the batch (over every
+    non-channel element, AG:276-284) is first lerped into running_var (weight 1 - momentum = 0.1, AG:315, 340) — the
+    entry of `sd` is REPLACED, so the caller sees the updated statistics, as the reference's buffer does."""
+    if sd.get(UPDATE_KEY, False):
+        var = x.reshape(-1, x.shape[-1]).var(dim=0, unbiased=False)
+        sd[p + "running_var"] = torch.lerp(sd[p + "running_var"], var, 0.1)
     s, t = batch_rms_affine(sd, p)
     return x * s + t
 

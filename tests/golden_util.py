@@ -86,3 +86,20 @@ def make_ref_head_inputs(case):
     pos[1, 1, -1:] = -1
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a).astype(np.int64))
     return t(seq), t(org), t(pos)
+
+
+# BatchRMSNorm with updating statistics (the reference's default; AG:324-361): two consecutive forwards with different
+# inputs, so the second one normalises with statistics the first one left behind
+UPDATE_CASE = dict(name="update_B2_L4096", B=2, L=4096, weight_seed=8)
+
+
+def make_update_inputs(case):
+    B, L = case["B"], case["L"]
+    rng = np.random.default_rng(77)
+    out = []
+    for step in range(2):
+        seq = rng.integers(0, 4, size=(B, L))
+        seq[0, 11 + step] = -1
+        org = (np.arange(B, dtype=np.int64) + step) % 2
+        out.append((torch.from_numpy(seq.astype(np.int64)), torch.from_numpy(org)))
+    return out

@@ -74,7 +74,7 @@ def main():
         return
 
     from alphagenome_b200.init_weights import apply_synth_weights
-    from alphagenome_b200.model import AlphaGenome, publication_heads_config
+    from alphagenome_b200.model import AlphaGenome, publication_heads_config, set_update_running_var
     from bench import N_SITES, synth_sites, synth_tokens
     from oracle import trunk_oracle as O
 
@@ -84,6 +84,7 @@ def main():
         for organism in ("human", "mouse"):
             model.add_heads(**publication_heads_config[organism])
     model = model.cuda().eval()
+    set_update_running_var(model, False)
     apply_synth_weights(model, seed=0)
     seq = synth_tokens(1, L)
     org = torch.zeros(1, dtype=torch.long)

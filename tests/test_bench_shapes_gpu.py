@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from alphagenome_b200.init_weights import apply_synth_weights
-from alphagenome_b200.model import AlphaGenome, publication_heads_config
+from alphagenome_b200.model import AlphaGenome, publication_heads_config, set_update_running_var
 from alphagenome_b200.trunk import engine_for
 from oracle import trunk_oracle as O
 
@@ -39,6 +39,7 @@ def test_cfg3_131k_trunk_and_publication_heads_vs_oracle():
     for organism in ("human", "mouse"):
         model.add_heads(**publication_heads_config[organism])
     model = model.cuda().eval()
+    set_update_running_var(model, False)
     apply_synth_weights(model, seed=7)
     rng = np.random.default_rng(131)
     seq = torch.from_numpy(rng.integers(0, 4, size=(B, L)).astype(np.int64))
@@ -74,6 +75,7 @@ def forward_1mbp():
     """One B200 forward at 1,048,576 bp with every stage output kept on the device."""
     L = 1_048_576
     model = AlphaGenome().cuda().eval()
+    set_update_running_var(model, False)
     apply_synth_weights(model, seed=9)
     seq = torch.from_numpy(np.random.default_rng(1).integers(0, 4, size=(1, L)).astype(np.int64))
     seq[0, 524_200:524_300] = -1

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from alphagenome_b200.init_weights import apply_synth_weights
-from alphagenome_b200.model import AlphaGenome, publication_heads_config
+from alphagenome_b200.model import AlphaGenome, publication_heads_config, set_update_running_var
 from tests.golden_util import HEAD_CASES, make_head_inputs, sample_rows
 
 pytestmark = pytest.mark.gpu
@@ -25,6 +25,7 @@ def model_with_heads(seed):
         for org in ("human", "mouse"):
             m.add_heads(**publication_heads_config[org])
         _M["m"] = m.cuda().eval()
+        set_update_running_var(_M["m"], False)
     apply_synth_weights(_M["m"], seed=seed)
     return _M["m"]
 
@@ -79,6 +80,7 @@ def test_custom_head_is_called_like_the_reference():
             return x.mean(dim=1)
 
     m = AlphaGenome().cuda().eval()
+    set_update_running_var(m, False)
     apply_synth_weights(m, seed=0)
     m.add_head("human", "mean128", MeanHead(), "embeds_128bp")
     seq = torch.randint(0, 4, (1, 2048), device="cuda")
@@ -132,6 +134,7 @@ def test_reference_heads_match_reference_golden(case):
     for o in ("human", "mouse"):
         m.add_reference_heads(o)
     m = m.cuda().eval()
+    set_update_running_var(m, False)
     apply_synth_weights(m, seed=case["weight_seed"])
     out = m(seq.cuda(), org.cuda(), splice_site_positions=pos.cuda())
     torch.cuda.synchronize()

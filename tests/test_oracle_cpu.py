@@ -143,3 +143,29 @@ def test_oracle_reference_heads_match_reference_golden(case):
         assert tuple(got.shape) == want.shape, (k, tuple(got.shape), want.shape)
         err = np.abs(got.numpy() - want).max() / float(g[k + "__absmax"])
         assert err < 5e-5, (k, err)
+
+
+def test_oracle_updating_batch_rmsnorm_matches_reference_golden():
+    """BatchRMSNorm with updating statistics (the reference's default, AG:324-361): two consecutive forwards of the
+    unmodified reference (tools/make_golden_update.py) — all 81 running_var buffers after each forward and the second
+    forward's embeddings."""
+    from tests.golden_util import UPDATE_CASE, make_update_inputs
+
+    g = np.load(GOLD / f"{UPDATE_CASE['name']}.npz")
+    sd = synth_sd(UPDATE_CASE["weight_seed"])
+    sd[O.UPDATE_KEY] = True
+    rv_keys = [k for k in sd if isinstance(k, str) and k.endswith("running_var")]
+    assert len(rv_keys) == 81
+    for step, (seq, org) in enumerate(make_update_inputs(UPDATE_CASE)):
+        before = {k: sd[k].clone() for k in rv_keys}
+        out = O.alphagenome_embeds(sd, seq, org)
+        for k in rv_keys:
+            want = g[f"rv{step}/{k}"]
+            assert not torch.equal(sd[k], before[k]), k                      # every norm on the path was updated
+            np.testing.assert_allclose(sd[k].numpy(), want, rtol=2e-4, atol=1e-6, err_msg=f"step {step} {k}")
+    for name in ("embeds_1bp", "embeds_128bp", "embeds_pair"):
+        got = out[name]
+        idx = sample_rows(name, got.shape)
+        got = (got if idx is None else got[:, idx]).numpy()
+        err = np.abs(got - g[name]).max() / float(g[name + "__absmax"])
+        assert err < 5e-5, (name, err)

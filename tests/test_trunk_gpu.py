@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from alphagenome_b200.init_weights import apply_synth_weights
-from alphagenome_b200.model import AlphaGenome
+from alphagenome_b200.model import AlphaGenome, set_update_running_var
 from alphagenome_b200.trunk import engine_for
 from oracle import trunk_oracle as O
 from tests.golden_util import CASES, make_inputs, sample_rows
@@ -24,6 +24,7 @@ _MODEL = {}
 def model_with_seed(seed):
     if "m" not in _MODEL:
         _MODEL["m"] = AlphaGenome().cuda().eval()
+        set_update_running_var(_MODEL["m"], False)   # frozen statistics, like the goldens (tools/make_golden.py)
     apply_synth_weights(_MODEL["m"], seed=seed)
     return _MODEL["m"]
 
@@ -123,6 +124,27 @@ def test_sequence_parallel_matches_single_rank():
     assert rec["ok"], rec
 
 
+def test_sequence_parallel_updating_batch_rmsnorm():
+    """Sharded forward with BatchRMSNorm re-estimating its variance (the reference's default): every rank contributes
+    its rows' sums through one all-reduce per norm, so the 81 updated running_var buffers and the outputs equal the
+    unsharded forward's (get_maybe_dist_var, AG:276-300)."""
+    import json
+    import subprocess
+    import sys
+
+    root = Path(__file__).resolve().parent.parent
+    same = torch.cuda.device_count() < 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", str(root / "tools" / "sp_check.py"), "--length", "16384", "--batch", "2", "--update-norms"]
+    if same:
+        cmd.append("--same-gpu")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("SP_CHECK ")]
+    assert lines, (p.returncode, p.stdout[-2000:], p.stderr[-3000:])
+    rec = json.loads(lines[-1][9:])
+    assert rec["ok"] and rec["running_var"]["updated"] == 81, rec
+
+
 def test_host_pipeline_matches_direct_calls():
     """HostPipeline (double-buffered H2D / forward / D2H) returns, per step, exactly what model(dna, org) returns."""
     import numpy as np
@@ -132,6 +154,7 @@ def test_host_pipeline_matches_direct_calls():
     from alphagenome_b200.pipeline import HostPipeline
 
     model = AlphaGenome().cuda().eval()
+    set_update_running_var(model, False)
     apply_synth_weights(model, seed=3)
     model.enable_cuda_graphs(True)
     rng = np.random.default_rng(5)
@@ -168,6 +191,7 @@ def test_alternating_shapes_keep_their_graphs_and_heads_forward_is_graphed():
     model = AlphaGenome()
     model.add_heads(**publication_heads_config["mouse"])
     model = model.cuda().eval()
+    set_update_running_var(model, False)
     apply_synth_weights(model, seed=2)
     eng = engine_for(model.transformer_unet, model)
     rng = np.random.default_rng(8)

@@ -17,7 +17,7 @@ import torch
 import torch.distributed as dist
 
 from alphagenome_b200.init_weights import apply_synth_weights
-from alphagenome_b200.model import AlphaGenome
+from alphagenome_b200.model import AlphaGenome, set_update_running_var
 from alphagenome_b200.parallel import SeqParallel
 from alphagenome_b200.trunk import engine_for
 
@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--length", type=int, default=32768)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--same-gpu", action="store_true")
+    ap.add_argument("--update-norms", action="store_true", help="BatchRMSNorm re-estimates running_var (the reference's default): also compares the 81 updated buffers")
     ap.add_argument("--heads", action="store_true", help="also run the publication heads of both organisms sharded vs unsharded")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -34,6 +35,7 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("gloo" if args.same_gpu else "nccl", **({} if args.same_gpu else dict(device_id=dev)))
     model = AlphaGenome().to(dev).eval()
+    set_update_running_var(model, args.update_norms)
     apply_synth_weights(model, seed=4)
     B, L = args.batch, args.length
     seq = torch.from_numpy(np.random.default_rng(11).integers(0, 4, size=(B, L)).astype(np.int64))
@@ -42,8 +44,13 @@ def main():
     org = (torch.arange(B) % 2).to(dev)
     eng = engine_for(model.transformer_unet, model)
     eng.sp = SeqParallel()
+    rv_names = [k for k in model.state_dict() if k.endswith("running_var")]
+    rv0 = {k: model.state_dict()[k].clone() for k in rv_names}
     emb, tu = model.get_embeds(seq, org, return_unet_transformer_outputs=True)
     torch.cuda.synchronize()
+    rv_sharded = {k: model.state_dict()[k].clone() for k in rv_names}
+    for k in rv_names:      # the unsharded forward below starts from the same statistics
+        model.state_dict()[k].copy_(rv0[k])
     shard = dict(embeds_1bp=emb.embeds_1bp, embeds_128bp=emb.embeds_128bp, embeds_pair=emb.embeds_pair,
                  unet_output=tu.unet_output, single_repr=tu.single_repr, pairwise_repr=tu.pairwise_repr)
     ncoll = eng.sp.n_collectives
@@ -97,10 +104,18 @@ def main():
         # propagates like any other bf16 noise of the forward (measured 2e-3..8e-3 of max at 8 ranks, 512 k bp) —
         # the bound is the north-star tolerance.
         ok = all(v <= 1e-2 for v in rep.values())
+        rv_rep = None
+        if args.update_norms:
+            # every BatchRMSNorm re-estimated its variance from the WHOLE context (one all-reduce of the shards' sums)
+            sd_full = model.state_dict()
+            changed = sum(int(not torch.equal(sd_full[k], rv0[k])) for k in rv_names)
+            worst = max(((rv_sharded[k] - sd_full[k]).abs() / sd_full[k].abs().clamp(min=1e-6)).max().item() for k in rv_names)
+            rv_rep = dict(buffers=len(rv_names), updated=changed, max_rel_diff_sharded_vs_unsharded=worst)
+            ok = ok and changed == len(rv_names) and worst <= 1e-2
         if head_rep is not None:
             ok = ok and all(v <= 3e-2 for v in head_rep.values())
             print("SP_HEADS " + json.dumps(head_rep), flush=True)
-        print("SP_CHECK " + json.dumps(dict(ok=ok, bitwise=all(v == 0.0 for v in rep.values()), world=world, L=L, B=B, collectives=ncoll, max_rel_diff=rep)), flush=True)
+        print("SP_CHECK " + json.dumps(dict(ok=ok, bitwise=all(v == 0.0 for v in rep.values()), world=world, L=L, B=B, collectives=ncoll, max_rel_diff=rep, **({'running_var': rv_rep} if rv_rep else {}))), flush=True)
     # leave without a collective teardown: a barrier/destroy after rank 0's extra (unsharded) forward once hung the
     # 2-GPU check until its timeout; every result is already printed
     torch.cuda.synchronize()
