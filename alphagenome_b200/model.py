@@ -22,6 +22,15 @@ from torch import nn
 TransformerUnetOutput = namedtuple("TransformerUnetOutput", ["unet_output", "single_repr", "pairwise_repr"])
 Embeds = namedtuple("Embeds", ["embeds_1bp", "embeds_128bp", "embeds_pair"])
 
+class EmbedsWithOperands(Embeds):
+    """Embeds (same three fields, unpacks the same) that also carries the bf16 tensor-core operands of the embeddings."""
+
+    def __new__(cls, embeds_1bp, embeds_128bp, embeds_pair, operands=None):
+        self = super().__new__(cls, embeds_1bp, embeds_128bp, embeds_pair)
+        self.operands = operands or {}
+        return self
+
+
 # AG:57-74 — kept verbatim as data so add_heads(**publication_heads_config[organism]) keeps working
 publication_heads_config = {
     "human": dict(organism="human", num_tracks_1bp=3165, num_tracks_128bp=2733, num_tracks_contacts=28,
@@ -408,6 +417,25 @@ class AlphaGenome(nn.Module):
             self.dim_1bp, H.jax_splice_junction_hidden_dim if splice_junction_hidden_dim is None else splice_junction_hidden_dim,
             H.jax_splice_junction_max_tissues if splice_junction_max_tissues is None else splice_junction_max_tissues))
 
+    def load_from_official_jax_model(self, model_version="all_folds", use_gpu=True, strict=False, params=None, state=None):
+        """AG:1733-1752: load the official JAX/Haiku checkpoint.  `params` / `state` (flat or nested Haiku trees) may be
+        handed in directly; otherwise they are fetched with alphagenome_research's loader like the reference does
+        (needs jax + alphagenome_research + network — none of which this package depends on)."""
+        from .convert import convert_checkpoint, flatten
+
+        if params is None:
+            try:
+                import jax
+                from alphagenome_research.model.dna_model import create_from_huggingface
+            except ImportError as e:
+                print(f"Error: Missing required dependency for conversion. Details: {e}")
+                return
+            device = jax.devices("gpu" if use_gpu else "cpu")[0]
+            jm = create_from_huggingface(model_version=model_version, device=device)
+            params, state = flatten(jm._params), flatten(jm._state)
+        self.load_state_dict(convert_checkpoint(params, state or {}), strict=strict)
+        return self
+
     def _heads(self):
         from .heads import HeadsEngine
 
@@ -449,10 +477,19 @@ class AlphaGenome(nn.Module):
         organism_index = self._organism_tensor(seq, organism_index).to(seq.device).long()
         eng = engine_for(self.transformer_unet, self)
         if embeds is None:
-            out = eng.run_embeds(seq, organism_index, want_head_operands=len(self.heads) != 0)
-            embeds = Embeds(out["embeds_1bp"], out["embeds_128bp"], out["embeds_pair"])
+            want = len(self.heads) != 0
+            if self.cuda_graphs:
+                out = eng.run_graphed(("embeds", want), lambda seq, org: eng.run_embeds(seq, org, want_head_operands=want),
+                                      dict(seq=seq.to(torch.int64), org=organism_index))
+            else:
+                out = eng.run_embeds(seq, organism_index, want_head_operands=want)
+            # the bf16 head operands the trunk's last epilogues wrote travel with the embeddings, so handing them back
+            # (embeds=...) reproduces this call's head outputs bit for bit
+            embeds = EmbedsWithOperands(out["embeds_1bp"], out["embeds_128bp"], out["embeds_pair"],
+                                        operands={k: out[k] for k in ("embeds_1bp_b16", "embeds_128bp_b16") if k in out})
         else:
             out = dict(embeds_1bp=embeds[0], embeds_128bp=embeds[1], embeds_pair=embeds[2])
+            out.update(getattr(embeds, "operands", None) or {})
         if len(self.heads) == 0:
             return embeds if return_embeds else {}
         plan = eng.sp.plan(seq.shape[1]) if eng.sp is not None else None
@@ -460,6 +497,16 @@ class AlphaGenome(nn.Module):
                                 track_masks=track_masks)
         res = {o: h for o, h in res.items() if h}                                   # AG:1963
         return (res, embeds) if return_embeds else res
+
+    @torch.no_grad()
+    def score_variant(self, seq_ref, seq_alt, organism_index, scorer, settings, variant, interval, track_metadata, organism=None,
+                      requested_heads=None, track_masks=None, **head_kwargs):
+        """AG:2003-2346: both alleles through the model (one batched forward), then scorer.get_masks_and_metadata ->
+        scorer.score_variant -> scorer.finalize_variant."""
+        from .dna_model import run_score_variant
+
+        return run_score_variant(self, seq_ref, seq_alt, organism_index, scorer, settings, variant, interval, track_metadata,
+                                 organism=organism, requested_heads=requested_heads, track_masks=track_masks, **head_kwargs)
 
     def _apply_track_mask(self, head_output, mask):
         from .heads import apply_track_mask

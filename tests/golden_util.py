@@ -103,3 +103,15 @@ def make_update_inputs(case):
         org = (np.arange(B, dtype=np.int64) + step) % 2
         out.append((torch.from_numpy(seq.astype(np.int64)), torch.from_numpy(org)))
     return out
+
+
+# DNAModel callers: predict with the two-pass splice flow and in-silico mutagenesis
+DNA_MODEL_CASE = dict(name="dna_model_L2048", L=2048, weight_seed=10, num_splice_sites=16, threshold=0.0, ism_batch=5)
+
+
+def make_dna_model_inputs(case):
+    """A DNA string with a few N and the positions to mutate (one of them on an N, one at each end)."""
+    rng = np.random.default_rng(55)
+    s = np.array(list("ACGT"))[rng.integers(0, 4, size=case["L"])]
+    s[700:704] = "N"
+    return "".join(s), [0, 5, 701, 1023, 1024, case["L"] - 1]
