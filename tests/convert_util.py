@@ -66,3 +66,52 @@ def synth_checkpoint(model, seed: int = 0):
             if k not in dst:   # multi-organism head arrays are shared by both organisms' rules
                 dst[k] = _rand(k, shape, seed, positive=k.endswith("var_ema"))
     return params, state
+
+
+def checkpoint_from_state_dict(sd, n_org: int = 2):
+    """The inverse problem: a JAX-layout checkpoint whose conversion reproduces `sd` (a PyTorch state_dict with the
+    checkpoint's heads for both organisms) — used to drive the conversion path with a WELL-BEHAVED weight distribution
+    (alphagenome_b200.init_weights).  Exact for every rule except the standardized convs, whose kernels come back
+    centred per output channel (the bake always centres): scale is chosen as sqrt(fan_in * var) so that nothing else
+    changes."""
+    params, state = {}, {}
+    per_org = {}
+    for rule in build_rules():
+        if rule.torch_key not in sd:
+            continue
+        t = sd[rule.torch_key].detach().float().cpu()
+        dst = state if rule.state else params
+        op = rule.op
+        if op == "concat":
+            outs = [x.t().contiguous() for x in torch.split(t, concat_split(rule.torch_key, t.shape[0]), dim=0)]
+        elif op == "stack":
+            outs = list(t.unbind(0))
+        elif op == "copy":
+            outs = [t]
+        elif op == "linear":
+            outs = [t.t().contiguous()]
+        elif op == "conv":
+            outs = [t.permute(2, 1, 0).contiguous()]
+        elif op == "pointwise":
+            outs = [t.squeeze(-1).t().contiguous()]
+        elif op == "squeeze":
+            outs = [t.reshape(1, 1, -1)]
+        elif op == "scalar":
+            outs = [t.reshape(())]
+        elif op == "standardized":
+            w = t.permute(2, 1, 0).contiguous()                       # (width, in, out)
+            var = (w - w.mean(dim=(0, 1), keepdim=True)).var(dim=(0, 1), keepdim=True, unbiased=False)
+            ex = dict(rule.extra)
+            dst[ex["scale"]] = torch.sqrt(w.shape[0] * w.shape[1] * var).numpy()
+            dst[ex["bias"]] = sd[rule.torch_key[: -len("weight")] + "bias"].detach().float().cpu().numpy()
+            outs = [w]
+        else:
+            raise ValueError(op)
+        for k, o in zip(rule.src, outs):
+            if rule.index is None:
+                dst[k] = o.numpy()
+            else:
+                per_org.setdefault(k, {})[rule.index] = o
+    for k, by in per_org.items():
+        params[k] = torch.stack([by[i] for i in range(n_org)], dim=0).numpy()
+    return params, state

@@ -47,15 +47,27 @@ def test_baked_standardized_conv_through_ag_gemm():
 
 
 def test_converted_checkpoint_runs_and_matches_oracle():
+    """A JAX-layout checkpoint (the inverse image of a well-behaved synthetic state_dict, so the weight distribution is
+    the one the north-star tolerance is stated for) -> convert -> load -> B200 forward + the checkpoint's heads."""
+    from alphagenome_b200.init_weights import apply_synth_weights
+    from tests.convert_util import checkpoint_from_state_dict
+
+    src = AlphaGenome()
+    for organism in ("human", "mouse"):
+        src.add_reference_heads(organism)
+    apply_synth_weights(src, seed=3)
+    params, state = checkpoint_from_state_dict(src.state_dict())
     model = AlphaGenome()
     for organism in ("human", "mouse"):
         model.add_reference_heads(organism)
-    params, state = synth_checkpoint(model, seed=3)
-    # a published checkpoint's norm gains are O(1): lift the synthetic scale / var_ema arrays so activations stay O(1)
-    for k in list(params):
-        if k.endswith("rms_batch_norm/scale") or k.endswith("/scale") and "norm" in k or k.endswith("standardized_conv1_d/scale"):
-            params[k] = (1.0 + params[k]).astype(np.float32)
     assert model.load_from_official_jax_model(params=params, state=state, strict=False) is model
+    # the conversion is the exact inverse except that baked conv kernels are centred per output channel
+    a, b = src.state_dict(), model.state_dict()
+    for k in a:
+        if k.endswith("net.2.weight") and a[k].shape[-1] > 1:
+            assert torch.allclose(b[k], a[k] - a[k].mean(dim=(1, 2), keepdim=True), atol=1e-6), k
+        elif a[k].is_floating_point():
+            assert torch.allclose(b[k], a[k], atol=1e-6), k
     model = model.cuda().eval()
     set_update_running_var(model, False)
     L = 4096
