@@ -49,8 +49,10 @@ enum : int { F_RES = 1, F_OUT = 2, F_ACTA = 4, F_ACTB = 8, F_POOL = 16, F_COUNT 
 struct GemmKParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmB2;                                     // W box of the LAST N tile (n_last wide); == tmB when uniform
   AgGemmArgs g;
   int n_tile, m_tiles, n_tiles, total_tiles, kblocks;   // m_tiles counts (128 * CG)-row tiles
+  int n_last;                                           // width of N tile n_tiles-1 (mixed-width tiling: k x n_tile + remainder)
   int a_bmask;                                          // 0 when A is shared by every batch (a_bstride == 0), else -1
   unsigned int* err;
 };
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmB2);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -179,7 +182,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   pdl_wait();                // ... and we read nothing from global memory before the previous kernel has completed
 
   const int iters = g.taps * p.kblocks;
-  const uint32_t b_bytes = (uint32_t)(p.n_tile / CG) * kBlockK * 2;   // this CTA's share of the W tile
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -192,7 +194,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         const int mt = rest % p.m_tiles;
         const int b = rest / p.m_tiles;
         const int row0 = g.a_row0 + (mt * CG + (int)crank) * kBlockM - g.taps / 2;
-        const int wrow0 = nt * p.n_tile + (int)crank * (p.n_tile / CG);
+        const bool last_n = nt == p.n_tiles - 1;
+        const int nw = last_n ? p.n_last : p.n_tile;                         // this tile's width
+        const CUtensorMap* tmB = last_n ? &p.tmB2 : &p.tmB;
+        const uint32_t b_bytes = (uint32_t)(nw / CG) * kBlockK * 2;          // this CTA's share of the W tile
+        const int wrow0 = nt * p.n_tile + (int)crank * (nw / CG);
         for (int tap = 0; tap < g.taps; ++tap) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u, 0x10u + stage, p.err);
@@ -200,11 +206,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
               // both CTAs' boxes complete on the leader's barrier, which expects the pair's bytes
               if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (kABytes + b_bytes));
               tma_load_3d_cg2(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b & p.a_bmask);
-              tma_load_3d_cg2(sB + stage * kBStage, &p.tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
+              tma_load_3d_cg2(sB + stage * kBStage, tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
               tma_load_3d(sA + stage * kABytes, &p.tmA, &full_bar[stage], kb * kBlockK, row0 + tap, b & p.a_bmask);
-              tma_load_3d(sB + stage * kBStage, &p.tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
+              tma_load_3d(sB + stage * kBStage, tmB, &full_bar[stage], kb * kBlockK, wrow0, g.w_batched ? b : tap);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -215,7 +221,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && crank == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM * CG, (uint32_t)p.n_tile);
+      const uint32_t idesc_full = make_idesc_bf16(kBlockM * CG, (uint32_t)p.n_tile);
+      const uint32_t idesc_last = make_idesc_bf16(kBlockM * CG, (uint32_t)p.n_last);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -223,6 +230,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[as], aphase ^ 1u, 0x30u + as, p.err);
         tc_fence_after();
+        const uint32_t idesc = (tile % p.n_tiles == p.n_tiles - 1) ? idesc_last : idesc_full;
         const uint32_t d_tmem = tmem_base + (uint32_t)as * kMaxNTile;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full_bar[stage], phase, 0x20u + stage, p.err);
@@ -268,9 +276,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     const bool a16 = g.actA.dtype == 0, b16 = g.actB.dtype == 0, p16 = g.actP.dtype == 0;
     const int aG = g.actA.act, bG = g.actB.act, pG = g.actP.act;
     const bool has_poolf = kPool && g.pool != nullptr, has_actP = kPool && g.actP.ptr != nullptr;
-    const int nchunks = p.n_tile / kEpiCols;
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       const int nt = tile % p.n_tiles;
+      const int nchunks = (nt == p.n_tiles - 1 ? p.n_last : p.n_tile) / kEpiCols;
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
@@ -423,10 +431,32 @@ static int forced_cg() {
   return g_gemm_cta_group.load();
 }
 
-static int pick_n_tile(int N) {
-  for (int t = 256; t >= 16; t -= 16)
-    if (N % t == 0) return t;
-  return 0;
+// N tiling.  The tensor pipe spends the same time on a 176/192/224-wide tile as on a 256-wide one (measured: ~510 clk
+// per 64-deep K block for every width in (128, 256]), so N is cut into 256-wide tiles plus ONE narrower remainder tile
+// (a multiple of 16 per CTA) instead of the largest divisor of N: 1152 = 4 x 256 + 128 (was 6 x 192), 1408 = 5 x 256 +
+// 128 (was 8 x 176), 896 = 3 x 256 + 128 (was 4 x 224).  env AGB_GEMM_UNIFORM=1 restores the divisor tiling (A/B timing).
+static bool uniform_tiles() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_GEMM_UNIFORM");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+static void pick_n_tiles(int N, int cg, int* n_tile, int* n_tiles, int* n_last) {
+  if (N % kMaxNTile == 0 || N < kMaxNTile || uniform_tiles() || (N % kMaxNTile) % (16 * cg) != 0) {
+    int t = kMaxNTile;
+    for (; t >= 16; t -= 16)
+      if (N % t == 0) break;
+    *n_tile = t < 16 ? 0 : t;
+    *n_tiles = t < 16 ? 0 : N / t;
+    *n_last = *n_tile;
+    return;
+  }
+  *n_tile = kMaxNTile;
+  *n_tiles = N / kMaxNTile + 1;
+  *n_last = N % kMaxNTile;
 }
 
 int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
@@ -464,12 +494,11 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   GemmKParams p;
   memset(&p, 0, sizeof(p));
   p.g = a;
-  p.n_tile = pick_n_tile(a.N);
-  if (!p.n_tile) return set_error("ag_gemm_fwd: no N tile for N=%d", a.N);
   int cg = forced_cg();
   if (cg == 0) cg = a.M > kBlockM ? 2 : 1;
+  pick_n_tiles(a.N, cg, &p.n_tile, &p.n_tiles, &p.n_last);
+  if (!p.n_tile) return set_error("ag_gemm_fwd: no N tile for N=%d", a.N);
   p.m_tiles = (a.M + kBlockM * cg - 1) / (kBlockM * cg);
-  p.n_tiles = a.N / p.n_tile;
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
   p.kblocks = (a.K + kBlockK - 1) / kBlockK;
   p.err = device_error_word(device);
@@ -488,6 +517,8 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
     uint64_t strides[2] = {(uint64_t)a.w_ld * 2, (uint64_t)(nz > 1 ? a.w_zstride : (int64_t)a.w_ld * (a.w_rows > 0 ? a.w_rows : a.N)) * 2};
     uint32_t box[3] = {kBlockK, (uint32_t)(p.n_tile / cg), 1};   // a CTA of a pair stages half of the W tile
     if (int rc = make_tensor_map_bf16(&p.tmB, a.W, 3, dims, strides, box)) return rc;
+    box[1] = (uint32_t)(p.n_last / cg);
+    if (int rc = make_tensor_map_bf16(&p.tmB2, a.W, 3, dims, strides, box)) return rc;
   }
 
   const int flags = (a.res ? F_RES : 0) | (a.out ? F_OUT : 0) | (a.actA.ptr ? F_ACTA : 0) | (a.actB.ptr ? F_ACTB : 0) |

@@ -147,5 +147,11 @@ CASES = [
     dict(name="pair_n176_full_epi", batch=2, M=768, K=320, N=1408, epilogue="full"),
     dict(name="pair_deep_k", batch=1, M=512, K=3072, N=1536),
     dict(name="pair_n16", batch=1, M=4096, K=128, N=16),
+    # mixed-width N tiling (k x 256 + one remainder tile): remainders 128 / 64 / 32 / 16 (the last one only tiles that way
+    # with single-CTA MMAs; CTA pairs fall back to the divisor tiling), with every epilogue output and with conv taps
+    dict(name="mixed_n1152_conv5_full_epi", batch=1, M=640, K=256, N=1152, taps=5, epilogue="full"),
+    dict(name="mixed_n288_relu", batch=2, M=300, K=128, N=288, epilogue="relu_bf16"),
+    dict(name="mixed_n272", batch=1, M=260, K=64, N=272),
+    dict(name="mixed_n832_batched", batch=3, M=200, K=128, N=832, w_batched=True),
     dict(name="shared_a_batched_w", batch=6, M=128, K=128, N=48, w_batched=True, a_shared=True, epilogue="relu_bf16"),
 ]
