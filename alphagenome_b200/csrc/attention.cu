@@ -41,8 +41,11 @@ constexpr int kAttVBytesMax = kAttMaxDv * kAttBN * 2;   // 48 KB
 constexpr int kAttXchBytes = 4 * kAttBM * 4;            // row max / row sum exchange between column quarters
 constexpr int kAttSmxWarps = 16;
 constexpr int kAttThreads = 64 + kAttSmxWarps * 32;
+// K ring: 4 stages.  Mode 0 streams 64+ key blocks through it (two more loads in flight than the first version's
+// 2-stage ring).  Mode 1 (<= 512 keys = 4 blocks) loads every K block ONCE and keeps it resident for both passes.
+constexpr int kAttKStages = 4;
 // the dynamic smem window of a CTA without static smem starts 1024-aligned (checked at kernel entry)
-constexpr int kAttSmem = 2 * kAttKBytes + 2 * kAttVBytesMax + kAttXchBytes + 256;
+constexpr int kAttSmem = kAttKStages * kAttKBytes + 2 * kAttVBytesMax + kAttXchBytes + 256;   // 231,680 B <= 227 KB
 constexpr uint32_t kTmemO = 256, kTmemQ = 448;
 
 struct AttnKParams {
@@ -88,19 +91,19 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
   const AgAttnArgs& a = p.a;
 
   uint8_t* sK = smem;
-  uint8_t* sV = sK + 2 * kAttKBytes;
+  uint8_t* sV = sK + kAttKStages * kAttKBytes;
   float* xch = reinterpret_cast<float*>(sV + 2 * kAttVBytesMax);   // [4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kAttVBytesMax + kAttXchBytes);
   uint64_t* q_full = bars;         // [1]  Q rows are in TMEM (16 softmax warps arrive)
-  uint64_t* k_full = bars + 1;     // [2]
-  uint64_t* k_empty = bars + 3;    // [2]
-  uint64_t* v_full = bars + 5;     // [2]
-  uint64_t* v_empty = bars + 7;    // [2]
-  uint64_t* s_full = bars + 9;     // [2]
-  uint64_t* s_empty = bars + 11;   // [2]
-  uint64_t* p_full = bars + 13;    // [2 S stages][2 key halves]
-  uint64_t* o_full = bars + 17;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* k_full = bars + 1;     // [kAttKStages]
+  uint64_t* k_empty = bars + 5;    // [kAttKStages]
+  uint64_t* v_full = bars + 9;     // [2]
+  uint64_t* v_empty = bars + 11;   // [2]
+  uint64_t* s_full = bars + 13;    // [2]
+  uint64_t* s_empty = bars + 15;   // [2]
+  uint64_t* p_full = bars + 17;    // [2 S stages][2 key halves]
+  uint64_t* o_full = bars + 21;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,6 +122,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
   const int nblk = crank == 0 ? nblk_lo : p.nblk - nblk_lo;
   const int npre = a.mode == 1 ? nblk : 0;
   const int nsteps = npre + nblk;
+  // mode 1 with at most kAttKStages key blocks: pass 2 re-reads the K tiles pass 1 left in shared memory
+  const bool k_res = a.mode == 1 && nblk <= kAttKStages;
   const uint32_t v_bytes = (uint32_t)dv * kAttBN * 2;
 
   if (warp == 0 && lane == 0) {
@@ -129,9 +134,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, kAttSmxWarps);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAttKStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
@@ -160,11 +167,13 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     if (lane == 0) {
       for (int s = 0; s < nsteps; ++s) {
         const int kb = kb0 + (s < npre ? s : s - npre);
-        const int st = s & 1;
-        mbar_wait(&k_empty[st], ((s >> 1) & 1) ^ 1u, 0x110u + st, p.err);
-        mbar_arrive_expect_tx(&k_full[st], kAttKBytes);
-        tma_load_4d(sK + st * kAttKBytes, &p.tmK, &k_full[st], 0, kb * kAttBN, hk, b);
-        tma_load_4d(sK + st * kAttKBytes + kAttKBytes / 2, &p.tmK, &k_full[st], 64, kb * kAttBN, hk, b);
+        if (!(k_res && s >= npre)) {
+          const int st = s & (kAttKStages - 1);
+          mbar_wait(&k_empty[st], ((s / kAttKStages) & 1) ^ 1u, 0x110u + st, p.err);
+          mbar_arrive_expect_tx(&k_full[st], kAttKBytes);
+          tma_load_4d(sK + st * kAttKBytes, &p.tmK, &k_full[st], 0, kb * kAttBN, hk, b);
+          tma_load_4d(sK + st * kAttKBytes + kAttKBytes / 2, &p.tmK, &k_full[st], 64, kb * kAttBN, hk, b);
+        }
         if (s >= npre) {
           const int f = s - npre;
           const int vs = f & 1;
@@ -185,17 +194,19 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       tc_fence_after();
       for (int s = 0; s <= nsteps; ++s) {
         if (s < nsteps) {
-          const int st = s & 1;
-          mbar_wait(&k_full[st], (s >> 1) & 1, 0x130u + st, p.err);
+          const int st = s & 1;                                                   // S stage
+          const bool reuse = k_res && s >= npre;                                  // K tile already resident (pass 2)
+          const int kst = k_res ? (s < npre ? s : s - npre) : (s & (kAttKStages - 1));   // K stage
+          if (!reuse) mbar_wait(&k_full[kst], (s / kAttKStages) & 1, 0x130u + kst, p.err);
           mbar_wait(&s_empty[st], ((s >> 1) & 1) ^ 1u, 0x140u + st, p.err);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {   // 16 channels of d per MMA: 8 TMEM columns of Q, 32 B inside a K atom row
-            const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + st * kAttKBytes + (kk >> 2) * (kAttKBytes / 2)));
+            const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + kst * kAttKBytes + (kk >> 2) * (kAttKBytes / 2)));
             tc_mma_bf16_ts(tmem_S + (uint32_t)st * kAttBN, tmem_Q + (uint32_t)(8 * kk), dk + (uint64_t)(2 * (kk & 3)), idesc_s,
                            kk > 0 ? 1u : 0u);
           }
-          tc_commit(&k_empty[st]);
+          if (!k_res) tc_commit(&k_empty[kst]);   // resident tiles are never refilled
           tc_commit(&s_full[st]);
         }
         if (s >= 1 && (s - 1) >= npre) {

@@ -125,6 +125,35 @@ class SeqParallel:
             dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group)
         self.n_collectives += 1
 
+    class _Pending:
+        """An all-gather in flight on NCCL's stream; wait() orders the current stream after it and returns the result."""
+
+        def __init__(self, work, out, finish, keep=None):
+            self.work, self.out, self.finish = work, out, finish
+            self.keep = keep      # the send buffer stays referenced until the collective has been waited for
+
+        def wait(self):
+            if self.work is not None:
+                self.work.wait()
+            return self.finish(self.out)
+
+    def gather_rows_async(self, x: torch.Tensor) -> "SeqParallel._Pending":
+        """gather_rows that does not block the current stream: the collective runs on NCCL's own stream while the
+        caller keeps launching independent kernels; .wait() returns [B, world*rows_loc, C]."""
+        x = x.contiguous()
+        B, r, C = x.shape
+        out = torch.empty(self.world, B, r, C, dtype=x.dtype, device=x.device)
+
+        def finish(o):
+            return o.view(1, self.world * r, C) if B == 1 else o.permute(1, 0, 2, 3).reshape(B, self.world * r, C)
+
+        if self._stage and x.is_cuda:      # gloo test plumbing: host-staged, synchronous
+            self._all_gather(out, x)
+            return SeqParallel._Pending(None, out, finish)
+        work = dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group, async_op=True)
+        self.n_collectives += 1
+        return SeqParallel._Pending(work, out, finish, keep=x)
+
     def plan(self, L: int) -> ShardPlan:
         return shard_plan(L, self.world, self.rank, self.halo_bp)
 
@@ -147,6 +176,10 @@ class SeqParallel:
     def exchange_halos(self, xs, h: int):
         """Several [B, rows, C_i] tensors (any dtypes, same B and rows) in ONE collective: their edge rows are packed
         as bytes.  Returns [(left_i, right_i), ...] like exchange_halo."""
+        return self.exchange_halos_async(xs, h).wait()
+
+    def exchange_halos_async(self, xs, h: int) -> "SeqParallel._Pending":
+        """exchange_halos that leaves the current stream free until .wait()."""
         B, r = xs[0].shape[0], xs[0].shape[1]
         parts = []
         for x in xs:
@@ -155,19 +188,26 @@ class SeqParallel:
         packed = torch.cat(parts, dim=-1).contiguous() if len(parts) > 1 else parts[0]
         nb = packed.shape[-1]
         out = torch.empty(self.world, 2, B, h, nb, dtype=torch.uint8, device=packed.device)
-        self._all_gather(out, packed)
-        res, off = [], 0
-        for x in xs:
-            w = x.shape[2] * x.element_size()
+        shapes = [(x.dtype, x.shape[2], x.shape[2] * x.element_size()) for x in xs]
 
-            def take(side_rank, side):
-                return out[side_rank, side, :, :, off:off + w].contiguous().view(x.dtype).view(B, h, x.shape[2])
+        def finish(out):
+            res, off = [], 0
+            for dtype, C, w in shapes:
+                def take(side_rank, side):
+                    return out[side_rank, side, :, :, off:off + w].contiguous().view(dtype).view(B, h, C)
 
-            left = take(self.rank - 1, 1) if self.rank > 0 else None
-            right = take(self.rank + 1, 0) if self.rank < self.world - 1 else None
-            res.append((left, right))
-            off += w
-        return res
+                left = take(self.rank - 1, 1) if self.rank > 0 else None
+                right = take(self.rank + 1, 0) if self.rank < self.world - 1 else None
+                res.append((left, right))
+                off += w
+            return res
+
+        if self._stage and packed.is_cuda:
+            self._all_gather(out, packed)
+            return SeqParallel._Pending(None, out, finish)
+        work = dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=self.group, async_op=True)
+        self.n_collectives += 1
+        return SeqParallel._Pending(work, out, finish, keep=packed)
 
     def all_reduce_sum(self, x: torch.Tensor) -> torch.Tensor:
         """Sum over ranks (splice-junction head: each gathered site row is non-zero on exactly one rank)."""
@@ -180,6 +220,18 @@ class SeqParallel:
             dist.all_reduce(x, group=self.group)
         self.n_collectives += 1
         return x
+
+    def transpose_blocks_async(self, pair: torch.Tensor) -> "SeqParallel._Pending":
+        """transpose_blocks without blocking the current stream (the decoder runs while the blocks travel)."""
+        B, Pl, P, C = pair.shape
+        G = self.world
+        send = pair.view(B, Pl, G, Pl, C).permute(2, 0, 1, 3, 4).contiguous()
+        recv = torch.empty_like(send)
+        if self._stage and send.is_cuda:
+            return SeqParallel._Pending(None, self.transpose_blocks(pair), lambda o: o)
+        work = dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group, async_op=True)
+        self.n_collectives += 1
+        return SeqParallel._Pending(work, recv, lambda o: o, keep=send)
 
     def transpose_blocks(self, pair: torch.Tensor) -> torch.Tensor:
         """pair: this rank's rows [B, P_loc, P, C] -> pairT [world, B, P_loc, P_loc, C] with

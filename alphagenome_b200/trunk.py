@@ -390,7 +390,20 @@ class TrunkEngine:
             self._note(f"downs.{i}.pooled", x)
         return x, skips
 
-    def _pair_block(self, P, li, single, pair, plan=None):
+    def _pool_rows(self, P, li, single, plan=None):
+        """First step of the pair block: 16-token average pooling + RMSNorm (+ its erf-GELU) of `single` (AG:828-829, 852).
+        Sharded: the pooled rows of every rank are needed; the all-gather is started here and waited for in _pair_block,
+        so it travels while the attention projections of the same layer are computed."""
+        sp = P["layers"][li]["s2p"]
+        B, n_loc, D = single.shape
+        Pl = n_loc // sp["pool"]
+        xsg = torch.empty(2, B, Pl, D, device=single.device, dtype=torch.bfloat16)    # [0] normalised pooled rows, [1] their erf-GELU
+        ops.pool_rmsnorm(single, sp["nw"], sp["nb"], xsg[0], xsg[1], sp["pool"])
+        if plan is not None and plan.world > 1:
+            return self.sp.gather_rows_async(xsg.view(2 * B, Pl, D))
+        return xsg
+
+    def _pair_block(self, P, li, single, pair, plan=None, pooled=None):
         """SingleToPairwise + row attention + pair FF (AG:1019-1022).  With a ShardPlan, `single` holds this rank's
         tokens and `pair` its rows [B, P_loc, P, 128]; pooled rows are all-gathered, everything else is row-local."""
         L = P["layers"][li]
@@ -401,13 +414,13 @@ class TrunkEngine:
         f32 = dict(device=dev, dtype=torch.float32)
         pool, H, dp = sp["pool"], sp["heads"], sp["dp"]
         Pl = n_loc // pool                      # local rows
-        xsg = torch.empty(2, B, Pl, D, **bf)    # [0] normalised pooled rows, [1] their erf-GELU
-        ops.pool_rmsnorm(single, sp["nw"], sp["nb"], xsg[0], xsg[1], pool)
+        if pooled is None:
+            pooled = self._pool_rows(P, li, single, plan)
         if plan is not None and plan.world > 1:
-            g = self.sp.gather_rows(xsg.view(2 * B, Pl, D)).view(2, B, plan.P, D)
+            g = pooled.wait().view(2, B, plan.P, D)
             xs, xg, Pn, i0 = g[0], g[1], plan.P, plan.row_off
         else:
-            xs, xg, Pn, i0 = xsg[0], xsg[1], Pl, 0
+            xs, xg, Pn, i0 = pooled[0], pooled[1], Pl, 0
         qk_plain = torch.empty(B, Pn, 2 * H * dp, **bf)
         qk_bias = torch.empty(B, Pn, 2 * H * dp, **bf)
         ops.gemm(xs, sp["Wqk"], actA=Act(qk_plain), actB=Act(qk_bias, None, sp["relbias"]))
@@ -482,8 +495,10 @@ class TrunkEngine:
         bias_of = {}
         a_ff = torch.empty(B, n, D, **bf)
         for li, L in enumerate(layers):
-            if "s2p" in L:
-                pair = self._pair_block(P, li, single, pair, plan)
+            # Order inside a layer: the pair block (AG:1019-1022) and the attention projections both read only the layer's
+            # input, so the projections go first and — sequence parallel — their K/V all-gather, like the pooled-row
+            # gather before it, is in flight on NCCL's stream while the pair block runs on this one.
+            pooled = self._pool_rows(P, li, single, plan) if "s2p" in L else None
             at = L["attn"]
             Hh, d, dv = at["heads"], at["d"], at["dv"]
             qkv = torch.empty(B, n, Hh * d + d + dv, **f32)
@@ -492,8 +507,13 @@ class TrunkEngine:
             K = torch.empty(B, n, d, **bf)
             V = torch.empty(B, n, dv, **bf)
             ops.qkv_post(qkv, Q, K, V, cos_t, sin_t, at["qw"], at["qb"], at["kw"], at["kb"], at["vw"], at["vb"], Hh, d, dv)
+            kv_pending = None
             if sharded:  # K/V of every rank (AG:748 attends over the whole context); Q and the bias rows stay local
-                KV = self.sp.gather_rows(torch.cat((K, V), dim=-1))   # ONE all-gather per layer: [B, n_all, d + dv]
+                kv_pending = self.sp.gather_rows_async(torch.cat((K, V), dim=-1))   # ONE all-gather per layer: [B, n_all, d + dv]
+            if "s2p" in L:
+                pair = self._pair_block(P, li, single, pair, plan, pooled=pooled)
+            if sharded:
+                KV = kv_pending.wait()
                 K, V = KV[..., :d], KV[..., d:]                         # strided views (TMA / transpose take a row stride)
             nk = _round_up(n_all, 8)
             Vt = torch.empty(B, dv, nk, **bf)
@@ -591,11 +611,28 @@ class TrunkEngine:
         single_b16 = torch.empty(B, n, D, **bf) if with_embeds else None
         single, pair = self._tower(P, x, org_embed, Act(a_dec, u0["s"], u0["t"], ACT_GELU1702), single_b16, plan)
         x_dec = single
+        halo_pending = pairT_pending = None
         if sharded:
             # the decoder's receptive field reaches 6 tokens into the neighbours: fetch halo tokens of the tower
-            # output (fp32 residual + the pre-activated bf16 operand) and run the decoder on the extended window
+            # output (fp32 residual + the pre-activated bf16 operand), one collective for both; the pair blocks needed
+            # by the symmetrize of the pair output embedding (AG:1253) travel at the same time.  Both are in flight on
+            # NCCL's stream while the 128 bp output embedding (and, for the pair blocks, the whole decoder) runs here.
             ht = self.sp.halo_bp // 128
-            (l32, r32), (l16, r16) = self.sp.exchange_halos([single, a_dec], ht)   # one collective for both
+            halo_pending = self.sp.exchange_halos_async([single, a_dec], ht)
+            if with_embeds:
+                pairT_pending = self.sp.transpose_blocks_async(pair)
+        if with_embeds:
+            f32 = dict(device=dev, dtype=torch.float32)
+            o128, o1, op = P["out128"], P["out1"], P["outpair"]
+            t128 = o128["table"].index_select(0, organism_index)
+            e128 = torch.empty(B, n, o128["W"].shape[1], **f32)
+            e128_b16 = torch.empty(B, n, o128["W"].shape[1], **bf)
+            self._gemm(single_b16, o128["W"], pre_shift=o128["b"], actA=Act(e128, o128["s"], t128, ACT_GELU1702),
+                       actB=Act(e128_b16, o128["s"], t128, ACT_GELU1702))
+            skp = torch.empty(B, n, o1["Wskip"].shape[1], **f32)
+            ops.gemm(e128_b16, o1["Wskip"], out=skp)
+        if sharded:
+            (l32, r32), (l16, r16) = halo_pending.wait()
             x_dec = torch.cat([t for t in (l32, single, r32) if t is not None], dim=1)
             a_dec = torch.cat([t for t in (l16, a_dec, r16) if t is not None], dim=1)
         self._own = (plan.halo_left, plan.halo_left + plan.L_loc, seq.shape[1]) if sharded else None
@@ -607,15 +644,6 @@ class TrunkEngine:
                 unet_b16 = unet_b16[:, plan.halo_left:plan.halo_left + plan.L_loc]
         out = dict(unet_output=unet_out, single_repr=single, pairwise_repr=pair)
         if with_embeds:
-            f32 = dict(device=dev, dtype=torch.float32)
-            o128, o1, op = P["out128"], P["out1"], P["outpair"]
-            t128 = o128["table"].index_select(0, organism_index)
-            e128 = torch.empty(B, n, o128["W"].shape[1], **f32)
-            e128_b16 = torch.empty(B, n, o128["W"].shape[1], **bf)
-            self._gemm(single_b16, o128["W"], pre_shift=o128["b"], actA=Act(e128, o128["s"], t128, ACT_GELU1702),
-                     actB=Act(e128_b16, o128["s"], t128, ACT_GELU1702))
-            skp = torch.empty(B, n, o1["Wskip"].shape[1], **f32)
-            ops.gemm(e128_b16, o1["Wskip"], out=skp)
             Lfull = unet_out.shape[1]
             shift = int(math.log2(Lfull // n))
             assert (n << shift) == Lfull
@@ -624,9 +652,9 @@ class TrunkEngine:
             # prediction heads take embeds_1bp as a bf16 MMA operand: emitted by the same epilogue when asked for
             e1_b16 = torch.empty(B, Lfull, o1["W"].shape[1], **bf) if want_head_operands else None
             self._gemm(unet_b16, o1["W"], pre_shift=o1["b"], res=skp, res_shift=shift, actA=Act(e1, o1["s"], t1, ACT_GELU1702),
-                     actB=Act(e1_b16, o1["s"], t1, ACT_GELU1702) if want_head_operands else None)
+                       actB=Act(e1_b16, o1["s"], t1, ACT_GELU1702) if want_head_operands else None)
             epair = torch.empty_like(pair)
-            pairT = self.sp.transpose_blocks(pair) if sharded else None  # symmetrize needs pair[j, i] (AG:1253)
+            pairT = pairT_pending.wait() if sharded else None
             ops.pair_out_embed(pair, op["w"], op["b"], op["emb"].index_select(0, organism_index).contiguous(), epair, pairT=pairT)
             out.update(embeds_1bp=e1, embeds_128bp=e128, embeds_pair=epair, embeds_128bp_b16=e128_b16)
             if want_head_operands:
