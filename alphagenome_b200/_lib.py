@@ -43,7 +43,7 @@ class AgGemmArgs(C.Structure):
         ("K", C.c_int32),
         ("taps", C.c_int32),
         ("w_rows", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("cta_group", C.c_int32),
         ("pre_scale", C.c_void_p),
         ("pre_shift", C.c_void_p),
         ("relu", C.c_int32),

@@ -68,6 +68,21 @@ static int ensure_device(int device) {
   return 0;
 }
 
+// Makes `device` current for the duration of one entry point and restores the caller's device afterwards (the library
+// must not flip the current device under a host framework that tracks it).
+struct DeviceGuard {
+  int prev = -1;
+  int rc = 0;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    rc = ensure_device(device);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
 unsigned int* device_error_word(int device) { return g_err_dev[device]; }
 int sm_count(int device) { return g_sm_count[device]; }
 
@@ -129,7 +144,10 @@ int ag_version(void) { return AGB200_VERSION; }
 const char* ag_last_error(void) { return tl_error; }
 uint64_t ag_launch_count(void) { return g_launches.load(); }
 
-int ag_check_device(int device) { return ensure_device(device); }
+int ag_check_device(int device) {
+  DeviceGuard guard(device);
+  return guard.rc;
+}
 
 int ag_watchdog_status(int device, uint32_t out[4]) {
   if (device < 0 || device >= 64 || !g_err_host[device]) {
@@ -147,19 +165,22 @@ int ag_gemm_set_cta_group(int cta_group) {
 
 int ag_gemm_fwd(const AgGemmArgs* args, int device, void* stream) {
   if (!args) return set_error("ag_gemm_fwd: null args");
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_gemm(*args, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_attention_fwd(const AgAttnArgs* args, int device, void* stream) {
   if (!args) return set_error("ag_attention_fwd: null args");
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_attention(*args, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_onehot_im2col_fwd(const int64_t* tokens, void* out_bf16, int32_t B, int32_t L, int32_t width, int32_t n_base,
                          int32_t ld, int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_onehot_im2col(tokens, out_bf16, B, L, width, n_base, ld, device, static_cast<cudaStream_t>(stream));
 }
 
@@ -167,14 +188,16 @@ int ag_qkv_post_fwd(const float* qkv, void* Q, void* K, void* V, const float* co
                     const float* q_w, const float* q_b, const float* k_w, const float* k_b, const float* v_w,
                     const float* v_b, int32_t B, int32_t n, int32_t heads, int32_t d, int32_t dv, int device,
                     void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_qkv_post(qkv, Q, K, V, cos_tab, sin_tab, q_w, q_b, k_w, k_b, v_w, v_b, B, n, heads, d, dv, device,
                          static_cast<cudaStream_t>(stream));
 }
 
 int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t C, int64_t in_bstride, int32_t in_ld,
                       int64_t out_bstride, int32_t out_ld, int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_transpose_bf16(in, out, nb, R, C, in_bstride, in_ld, out_bstride, out_ld, device,
                                static_cast<cudaStream_t>(stream));
 }
@@ -182,14 +205,16 @@ int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t 
 int ag_pair_bias_fwd(const float* pair, const float* scale, const float* shift, const float* W, float* bias, int32_t B,
                      int32_t rows, int32_t cols, int32_t C, int32_t heads, int32_t sets, int64_t set_stride, int device,
                      void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_pair_bias(pair, scale, shift, W, bias, B, rows, cols, C, heads, sets, set_stride, device,
                           static_cast<cudaStream_t>(stream));
 }
 
 int ag_pool_rmsnorm_fwd(const float* single, const float* w, const float* b, void* x_bf16, void* xg_bf16, int32_t B,
                         int32_t n, int32_t C, int32_t pool, int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_pool_rmsnorm(single, w, b, x_bf16, xg_bf16, B, n, C, pool, device, static_cast<cudaStream_t>(stream));
 }
 
@@ -197,61 +222,70 @@ int ag_pair_combine_fwd(const float* qk, const float* relq, const float* relk, c
                         const float* outer, const float* prev, float* pair, const float* norm_w, const float* norm_b,
                         void* pair_norm_bf16, int32_t B, int32_t P, int32_t H, int32_t D, int32_t qk_ld, int32_t rel_ld,
                         int32_t rows, int32_t i_off, int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair, norm_w, norm_b, pair_norm_bf16, B, P, H, D, qk_ld,
                              rel_ld, rows, i_off, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_rmsnorm_fwd(const float* x, const float* w, const float* b, void* out_bf16, int64_t rows, int32_t C, int device,
                    void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_rmsnorm(x, w, b, out_bf16, rows, C, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_add_embed_norm_fwd(const float* x, const float* emb, const float* scale, const float* shift, float* single,
                           void* a_bf16, int32_t B, int32_t rows, int32_t C, int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_add_embed_norm(x, emb, scale, shift, single, a_bf16, B, rows, C, device,
                                static_cast<cudaStream_t>(stream));
 }
 
 int ag_pair_out_embed_fwd(const float* pair, const float* pairT, const float* w, const float* b, const float* emb,
                           float* out, int32_t B, int32_t rows, int32_t P, int32_t C, int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_pair_out_embed(pair, pairT, w, b, emb, out, B, rows, P, C, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_rmsnorm_act_fwd(const float* x, const float* w, const float* b, const float* add, void* out_bf16, int64_t rows,
                        int64_t rows_per_batch, int32_t C, int32_t act, int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_rmsnorm_act(x, w, b, add, out_bf16, rows, rows_per_batch, C, act, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_splice_rope_fwd(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
                        void* out_bf16, int32_t B, int32_t P, int32_t T, int32_t hidden, int32_t p_ld, int32_t tab_per_site,
                        int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_splice_rope(x, scale, offset, cos_tab, sin_tab, out_bf16, B, P, T, hidden, p_ld, tab_per_site, device,
                             static_cast<cudaStream_t>(stream));
 }
 
 int ag_bn_stats_fwd(const float* x, double* sums, int32_t B, int32_t rows, int64_t bstride, int32_t ld, int32_t C, int device,
                     void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_bn_stats(x, sums, B, rows, bstride, ld, C, device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_bn_update_fwd(const double* sums, double count, float* running_var, const float* gamma, float momentum, float eps,
                      float* scale_out, const float* fold_bias, const float* fold_beta, float* fold_shift_out, int32_t C,
                      int device, void* stream) {
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_bn_update(sums, count, running_var, gamma, momentum, eps, scale_out, fold_bias, fold_beta, fold_shift_out, C,
                           device, static_cast<cudaStream_t>(stream));
 }
 
 int ag_affine_act_fwd(const AgAffineArgs* args, int device, void* stream) {
   if (!args) return set_error("ag_affine_act_fwd: null args");
-  if (int rc = ensure_device(device)) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
   return launch_affine_act(*args, device, static_cast<cudaStream_t>(stream));
 }
 

@@ -355,6 +355,17 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     }
 
     // ---- epilogue: O / rowsum (+ bias + residual); each column quarter writes dv/4 of the columns ----
+    // Row-attention epilogue (fp32 out + residual + RMSNorm): this thread's 32 residual values are requested NOW, so the
+    // eight 16-byte loads (rows are 512 B apart: one sector each) are in flight while the last P.V MMAs drain, instead
+    // of eight exposed round trips inside the store loop (ncu: 40 % of the kernel's stall samples sat on those adds).
+    float4 rpre[8];
+    const bool pre_res = a.norm_out != nullptr && a.res != nullptr && row < a.n_q;
+    if (pre_res) {
+      const float* rs = a.res + ((long)b * a.out_bstride + (long)h * a.out_hstride + (long)row * a.out_ld) + cq * (dv / 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rpre[j].x), "=f"(rpre[j].y), "=f"(rpre[j].z), "=f"(rpre[j].w) : "l"(rs + 4 * j));
+    }
     xch[cq * 128 + lrow] = (rsum[0] + rsum[1]) + (rsum[2] + rsum[3]);
     asm volatile("bar.sync 1, 512;" ::: "memory");
     float rtot = (xch[lrow] + xch[128 + lrow]) + (xch[256 + lrow] + xch[384 + lrow]);
@@ -399,15 +410,14 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       float ss = 0.f;
       if (row < a.n_q) {
         float* o = reinterpret_cast<float*>(a.out) + obase + cbeg;
-        const float* rs = a.res ? a.res + obase + cbeg : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (a.out_bias) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(a.out_bias + cbeg + j));
             y[j] += bb.x; y[j + 1] += bb.y; y[j + 2] += bb.z; y[j + 3] += bb.w;
           }
-          if (rs) {
-            const float4 rr = *reinterpret_cast<const float4*>(rs + j);
+          if (pre_res) {
+            const float4 rr = rpre[j >> 2];
             y[j] += rr.x; y[j + 1] += rr.y; y[j + 2] += rr.z; y[j + 3] += rr.w;
           }
           *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);

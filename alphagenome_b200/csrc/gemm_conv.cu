@@ -120,9 +120,22 @@ __device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool i
   }
 }
 
+// Per-channel epilogue parameters are re-read by every tile: keep them in what little L1 the 226 KB of shared memory
+// leaves (evict_last), and let the residual rows — a pure stream, 64-128 KB per tile — bypass L1 (no_allocate).  ncu
+// (profiles/ncu_r02_summary.md): 39 % of the HBM-bound w1 GEMM's stall samples sat on the first use of pre_shift, an
+// L1 miss queued behind the residual stream that had evicted it.
 __device__ __forceinline__ float4 ldg4_or(const float* p, float dflt) {
-  if (p) return __ldg(reinterpret_cast<const float4*>(p));
+  if (p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+  }
   return make_float4(dflt, dflt, dflt, dflt);
+}
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 }
 
 template <int FLAGS, int CG>
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             const int lr = lr_base + 2 * rsel + ((k & 1) ^ (rsel & 1)) + 16 * (k >> 1);
             rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (on && lr < rows_left)
-              rr[k] = __ldg(reinterpret_cast<const float4*>(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col)));
+              rr[k] = ldg4_stream(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col));
           }
         }
         uint32_t r[16];
@@ -494,7 +507,8 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   GemmKParams p;
   memset(&p, 0, sizeof(p));
   p.g = a;
-  int cg = forced_cg();
+  if (a.cta_group < 0 || a.cta_group > 2) return set_error("ag_gemm_fwd: cta_group=%d must be 0, 1 or 2", a.cta_group);
+  int cg = a.cta_group ? a.cta_group : forced_cg();
   if (cg == 0) cg = a.M > kBlockM ? 2 : 1;
   pick_n_tiles(a.N, cg, &p.n_tile, &p.n_tiles, &p.n_last);
   if (!p.n_tile) return set_error("ag_gemm_fwd: no N tile for N=%d", a.N);

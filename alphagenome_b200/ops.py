@@ -33,8 +33,10 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: Optional[torch.Tensor] = None) -> int:
+    """The current stream OF THE TENSOR'S DEVICE (a model on cuda:1 launches on cuda:1's current stream even when the
+    process's current device is cuda:0)."""
+    return torch.cuda.current_stream(t.device if t is not None else None).cuda_stream
 
 
 def _require(cond: bool, msg: str) -> None:
@@ -95,6 +97,7 @@ def gemm(
     actB: Optional[Act] = None,
     pool: Optional[torch.Tensor] = None,
     actP: Optional[Act] = None,
+    cta_group: int = 0,
 ) -> None:
     """ag_gemm_fwd: conv1d (taps = W.shape[0]) / linear / batched matmul with the fused epilogue of agb200.h.
 
@@ -133,6 +136,7 @@ def gemm(
     g.w_ld = W.stride(1)
     g.batch, g.M, g.N, g.K, g.taps = batch, M, N, K, taps
     g.w_rows = w_rows
+    g.cta_group = int(cta_group)
     for name, v in (("pre_scale", pre_scale), ("pre_shift", pre_shift)):
         if v is not None:
             _require(v.dtype == torch.float32 and v.numel() == N and v.is_contiguous(), f"{name} must be fp32 [N]")
@@ -175,7 +179,7 @@ def gemm(
     if PROFILE_GEMM is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
+        _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream(A)))
         e1.record()
         # algorithmic bytes of this launch: every operand / output once at its storage dtype
         def _out_bytes(a, rows):
@@ -191,7 +195,7 @@ def gemm(
         nbytes += _out_bytes(actA, M) + _out_bytes(actB, M) + _out_bytes(actP, M // 2)
         PROFILE_GEMM.append((e0, e1, 2.0 * batch * M * (w_rows or N) * K * taps, float(nbytes)))
         return
-    _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream()))
+    _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream(A)))
 
 
 def set_gemm_cta_group(cta_group: int) -> int:
@@ -266,14 +270,14 @@ def attention(
         _f32(norm_b, "norm_b")
         _require(norm_w is not None and norm_b is not None and norm_w.numel() == dv and norm_b.numel() == dv, "norm_w/norm_b must be fp32 [dv]")
     a.norm_w, a.norm_b, a.norm_out = _ptr(norm_w), _ptr(norm_b), _ptr(norm_out)
-    _lib.check(lib.ag_attention_fwd(C.byref(a), _dev(Q), _stream()))
+    _lib.check(lib.ag_attention_fwd(C.byref(a), _dev(Q), _stream(Q)))
 
 
 def onehot_im2col(tokens: torch.Tensor, out: torch.Tensor, width: int, n_base: int) -> None:
     _require(tokens.is_cuda and tokens.dtype == torch.int64 and tokens.is_contiguous() and tokens.dim() == 2, "tokens must be CUDA int64 [B, L]")
     B, L = tokens.shape
     _require(out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape[:2]) == (B, L), "out must be bf16 [B, L, ld]")
-    _lib.check(_lib.load().ag_onehot_im2col_fwd(tokens.data_ptr(), out.data_ptr(), B, L, width, n_base, out.shape[2], _dev(out), _stream()))
+    _lib.check(_lib.load().ag_onehot_im2col_fwd(tokens.data_ptr(), out.data_ptr(), B, L, width, n_base, out.shape[2], _dev(out), _stream(out)))
 
 
 def qkv_post(qkv, Q, K, V, cos_tab, sin_tab, qw, qb, kw, kb, vw, vb, heads: int, d: int, dv: int) -> None:
@@ -286,7 +290,7 @@ def qkv_post(qkv, Q, K, V, cos_tab, sin_tab, qw, qb, kw, kb, vw, vb, heads: int,
         _require(t.dtype == torch.bfloat16 and t.is_contiguous(), "Q/K/V outputs must be contiguous bf16")
     _lib.check(_lib.load().ag_qkv_post_fwd(qkv.data_ptr(), Q.data_ptr(), K.data_ptr(), V.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(),
                                            qw.data_ptr(), qb.data_ptr(), kw.data_ptr(), kb.data_ptr(), vw.data_ptr(), vb.data_ptr(),
-                                           B, n, heads, d, dv, _dev(qkv), _stream()))
+                                           B, n, heads, d, dv, _dev(qkv), _stream(qkv)))
 
 
 def transpose_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -294,7 +298,7 @@ def transpose_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     _require(src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.dim() == 3 and dst.dim() == 3, "bf16 3-d views expected")
     nb, R, Cc = src.shape
     _require(dst.shape[0] == nb and dst.shape[1] == Cc and dst.shape[2] >= R and src.stride(2) == 1 and dst.stride(2) == 1, "transpose shape mismatch")
-    _lib.check(_lib.load().ag_transpose_bf16(src.data_ptr(), dst.data_ptr(), nb, R, Cc, src.stride(0), src.stride(1), dst.stride(0), dst.stride(1), _dev(src), _stream()))
+    _lib.check(_lib.load().ag_transpose_bf16(src.data_ptr(), dst.data_ptr(), nb, R, Cc, src.stride(0), src.stride(1), dst.stride(0), dst.stride(1), _dev(src), _stream(src)))
 
 
 def pair_bias(pair, scale, shift, W, bias_out) -> None:
@@ -309,7 +313,7 @@ def pair_bias(pair, scale, shift, W, bias_out) -> None:
     want = (sets, B, heads, rows, cols) if W.dim() == 3 else (B, heads, rows, cols)
     _require(tuple(bias_out.shape) == want, f"bias_out must be {want}")
     _lib.check(_lib.load().ag_pair_bias_fwd(pair.data_ptr(), scale.data_ptr(), shift.data_ptr(), W.data_ptr(), bias_out.data_ptr(), B, rows,
-                                            cols, Cc, heads, sets, B * heads * rows * cols, _dev(pair), _stream()))
+                                            cols, Cc, heads, sets, B * heads * rows * cols, _dev(pair), _stream(pair)))
 
 
 def pool_rmsnorm(single, w, b, x_out, xg_out, pool: int) -> None:
@@ -318,7 +322,7 @@ def pool_rmsnorm(single, w, b, x_out, xg_out, pool: int) -> None:
         _f32(t, nm)
     for t in (x_out, xg_out):
         _require(t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == (B, n // pool, Cc), "pooled outputs must be bf16 [B, n/pool, C]")
-    _lib.check(_lib.load().ag_pool_rmsnorm_fwd(single.data_ptr(), w.data_ptr(), b.data_ptr(), x_out.data_ptr(), xg_out.data_ptr(), B, n, Cc, pool, _dev(single), _stream()))
+    _lib.check(_lib.load().ag_pool_rmsnorm_fwd(single.data_ptr(), w.data_ptr(), b.data_ptr(), x_out.data_ptr(), xg_out.data_ptr(), B, n, Cc, pool, _dev(single), _stream(single)))
 
 
 def pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair_out, P: int, i_off: int = 0, norm_w=None, norm_b=None, norm_out=None) -> None:
@@ -337,7 +341,7 @@ def pair_combine(qk, relq, relk, Wp, bp, outer, prev, pair_out, P: int, i_off: i
         _require(norm_w is not None and norm_b is not None and norm_w.numel() == D and norm_b.numel() == D, "norm_w/norm_b must be fp32 [D]")
     _lib.check(_lib.load().ag_pair_combine_fwd(qk.data_ptr(), relq.data_ptr(), relk.data_ptr(), Wp.data_ptr(), bp.data_ptr(), outer.data_ptr(),
                                                _ptr(prev), pair_out.data_ptr(), _ptr(norm_w), _ptr(norm_b), _ptr(norm_out), B, P, H, D, qk.shape[3],
-                                               relq.shape[3], rows, i_off, _dev(qk), _stream()))
+                                               relq.shape[3], rows, i_off, _dev(qk), _stream(qk)))
 
 
 def rmsnorm(x, w, b, out) -> None:
@@ -346,7 +350,7 @@ def rmsnorm(x, w, b, out) -> None:
     for t, nm in ((x, "x"), (w, "w"), (b, "b")):
         _f32(t, nm)
     _require(out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() == x.numel(), "out must be contiguous bf16 of x's size")
-    _lib.check(_lib.load().ag_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, Cc, _dev(x), _stream()))
+    _lib.check(_lib.load().ag_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, Cc, _dev(x), _stream(x)))
 
 
 def add_embed_norm(x, emb, scale, shift, single_out, a_out) -> None:
@@ -354,7 +358,7 @@ def add_embed_norm(x, emb, scale, shift, single_out, a_out) -> None:
     for t, nm in ((x, "x"), (emb, "emb"), (scale, "scale"), (shift, "shift"), (single_out, "single_out")):
         _f32(t, nm)
     _require(tuple(emb.shape) == (B, Cc) and a_out.dtype == torch.bfloat16 and a_out.is_contiguous(), "emb must be [B, C]; a_out bf16")
-    _lib.check(_lib.load().ag_add_embed_norm_fwd(x.data_ptr(), emb.data_ptr(), scale.data_ptr(), shift.data_ptr(), single_out.data_ptr(), a_out.data_ptr(), B, rows, Cc, _dev(x), _stream()))
+    _lib.check(_lib.load().ag_add_embed_norm_fwd(x.data_ptr(), emb.data_ptr(), scale.data_ptr(), shift.data_ptr(), single_out.data_ptr(), a_out.data_ptr(), B, rows, Cc, _dev(x), _stream(x)))
 
 
 def pair_out_embed(pair, w, b, emb, out, pairT=None) -> None:
@@ -366,7 +370,7 @@ def pair_out_embed(pair, w, b, emb, out, pairT=None) -> None:
     for t, nm in ((pair, "pair"), (pairT, "pairT"), (w, "w"), (b, "b"), (emb, "emb"), (out, "out")):
         _f32(t, nm)
     _require(pairT.numel() == pair.numel(), "pairT size mismatch")
-    _lib.check(_lib.load().ag_pair_out_embed_fwd(pair.data_ptr(), pairT.data_ptr(), w.data_ptr(), b.data_ptr(), emb.data_ptr(), out.data_ptr(), B, rows, P, Cc, _dev(pair), _stream()))
+    _lib.check(_lib.load().ag_pair_out_embed_fwd(pair.data_ptr(), pairT.data_ptr(), w.data_ptr(), b.data_ptr(), emb.data_ptr(), out.data_ptr(), B, rows, P, Cc, _dev(pair), _stream(pair)))
 
 
 def rmsnorm_act(x, w, b, out, add=None, rows_per_batch: Optional[int] = None, act: int = ACT_NONE) -> None:
@@ -379,7 +383,7 @@ def rmsnorm_act(x, w, b, out, add=None, rows_per_batch: Optional[int] = None, ac
     if add is not None:
         _require(rows_per_batch is not None and add.shape[-1] == Cc and add.numel() // Cc * rows_per_batch == rows, "add must be [rows / rows_per_batch, C]")
     _lib.check(_lib.load().ag_rmsnorm_act_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), _ptr(add), out.data_ptr(), rows,
-                                              rows_per_batch or rows, Cc, int(act), _dev(x), _stream()))
+                                              rows_per_batch or rows, Cc, int(act), _dev(x), _stream(x)))
 
 
 def splice_rope(x, scale, offset, cos_tab, sin_tab, out) -> None:
@@ -395,7 +399,7 @@ def splice_rope(x, scale, offset, cos_tab, sin_tab, out) -> None:
              "scale/offset [T, H]; cos/sin [T, H/2] or [B, P, H/2]")
     _require(out.dtype == torch.bfloat16 and out.is_contiguous() and out.dim() == 4 and out.shape[0] == B and out.shape[1] == T and out.shape[2] >= P and out.shape[3] == Hd, "out must be bf16 [B, T, >=P, H]")
     _lib.check(_lib.load().ag_splice_rope_fwd(x.data_ptr(), scale.data_ptr(), offset.data_ptr(), cos_tab.data_ptr(), sin_tab.data_ptr(), out.data_ptr(),
-                                              B, P, T, Hd, out.shape[2], 1 if per_site else 0, _dev(x), _stream()))
+                                              B, P, T, Hd, out.shape[2], 1 if per_site else 0, _dev(x), _stream(x)))
 
 
 # ------------------------------------------------------------------------------------------------ updating BatchRMSNorm
@@ -406,7 +410,7 @@ def bn_stats(x: torch.Tensor, sums: torch.Tensor) -> None:
     B, rows, Cc = x.shape
     _require(sums.dtype == torch.float64 and sums.is_contiguous() and tuple(sums.shape) == (2, Cc), "sums must be fp64 [2, C]")
     bs = x.stride(0) if B > 1 else x.stride(1) * rows
-    _lib.check(_lib.load().ag_bn_stats_fwd(x.data_ptr(), sums.data_ptr(), B, rows, bs, x.stride(1), Cc, _dev(x), _stream()))
+    _lib.check(_lib.load().ag_bn_stats_fwd(x.data_ptr(), sums.data_ptr(), B, rows, bs, x.stride(1), Cc, _dev(x), _stream(x)))
 
 
 def bn_update(sums, count: float, running_var, gamma, momentum: float, eps: float, scale_out, fold_bias=None, fold_beta=None,
@@ -419,7 +423,7 @@ def bn_update(sums, count: float, running_var, gamma, momentum: float, eps: floa
         _require(t is None or t.numel() == Cc, f"{nm} must have C elements")
     _require(sums.dtype == torch.float64 and sums.is_contiguous() and sums.numel() == 2 * Cc, "sums must be fp64 [2, C]")
     _lib.check(_lib.load().ag_bn_update_fwd(sums.data_ptr(), float(count), running_var.data_ptr(), gamma.data_ptr(), float(momentum), float(eps),
-                                            scale_out.data_ptr(), _ptr(fold_bias), _ptr(fold_beta), _ptr(fold_shift_out), Cc, _dev(running_var), _stream()))
+                                            scale_out.data_ptr(), _ptr(fold_bias), _ptr(fold_beta), _ptr(fold_shift_out), Cc, _dev(running_var), _stream(running_var)))
 
 
 def affine_act(x, scale=None, shift=None, *, res=None, out_f32=None, out_bf16=None, act: int = ACT_NONE) -> None:
@@ -456,4 +460,4 @@ def affine_act(x, scale=None, shift=None, *, res=None, out_f32=None, out_bf16=No
         _require(o.dtype == torch.bfloat16 and tuple(o.shape) == (B, rows, Cc), "out_bf16 must be bf16 with x's shape")
         a.out_bf16, a.out_bf16_bstride, a.out_bf16_ld = o.data_ptr(), bst(o), o.stride(1)
     a.B, a.rows, a.C, a.act = B, rows, Cc, int(act)
-    _lib.check(_lib.load().ag_affine_act_fwd(C.byref(a), _dev(x), _stream()))
+    _lib.check(_lib.load().ag_affine_act_fwd(C.byref(a), _dev(x), _stream(x)))

@@ -90,7 +90,8 @@ typedef struct AgGemmArgs {
   int32_t K;          /* input channels (multiple of 8) */
   int32_t taps;       /* 1 or 5 (any odd value <= 15 is accepted) */
   int32_t w_rows;     /* rows of W present in memory (0 = N); rows in [w_rows, N) read as zero, so N can be padded to 16 */
-  int32_t reserved0;
+  int32_t cta_group;     /* CTAs per tcgen05.mma for THIS call: 0 = the process default (automatic unless ag_gemm_set_cta_group
+                          * changed it), 1 = single-CTA MMAs, 2 = CTA pairs (cta_group::2).  Same results either way. */
   const float* pre_scale; /* [N] or NULL */
   const float* pre_shift; /* [N] or NULL (bias, possibly folded with a post-norm) */
   int32_t relu;
@@ -269,9 +270,15 @@ int ag_check_device(int device);
 /* device watchdog: a kernel whose mbarrier wait exceeds ~4 s records {0xDEAD0000|tag, blockIdx, threadIdx, parity}
  * in host-mapped memory and traps (never hangs the GPU); returns non-zero if such a record exists. */
 int ag_watchdog_status(int device, uint32_t out[4]);
-/* tuning / bring-up hook with no reference counterpart: CTAs per tcgen05.mma in ag_gemm_fwd.  0 = automatic (CTA pairs,
- * cta_group::2, whenever the problem has at least two 128-row tiles), 1 = single-CTA MMAs, 2 = pairs.  Results are
- * bit-identical either way (same products, same fp32 accumulation order); returns the previous setting. */
+/* Process-wide tuning / bring-up state (no reference counterpart).  Everything else in this library is re-entrant and
+ * keeps no state between calls; these switches are the exception, are meant for A/B timing, and must not be changed
+ * while other threads are inside the library:
+ *   - ag_gemm_set_cta_group: default CTAs per tcgen05.mma in ag_gemm_fwd for calls that leave AgGemmArgs.cta_group = 0.
+ *     0 = automatic (CTA pairs whenever the problem has at least two 128-row tiles), 1, 2.  Results are bit-identical
+ *     either way (same products, same fp32 accumulation order); returns the previous setting.
+ *   - environment variables read ONCE per process: AGB_GEMM_CG (seeds the default above), AGB_GEMM_UNIFORM=1 (divisor
+ *     N tiling instead of 256-wide tiles + remainder), AGB_ATTN_POLY (exponentials per 8 on the FMA pipe),
+ *     AGB_ATTN_SPLIT (force the attention key split off / on), AGB_PDL=0 (no programmatic dependent launch). */
 int ag_gemm_set_cta_group(int cta_group);
 
 #ifdef __cplusplus

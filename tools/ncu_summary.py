@@ -1,5 +1,9 @@
 """Key metrics of every launch in an .ncu-rep (`ncu --set full` capture) as a markdown table.
-Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep"""
+Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--csv profiles/x.csv] [--traffic-json profiles/gemm_traffic.json --note "..."]
+
+--csv            also write the raw metric table (`ncu --page raw --csv`) next to the summary (tracked evidence)
+--traffic-json   write {dram_bytes_per_launch, duration_us, kernel, source, note} of launch 0: what bench.py reports as
+                 roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM shape)"""
 import csv
 import io
 import subprocess
@@ -40,6 +44,22 @@ def main():
             i = col[m]
             cells.append(f"{r[i]} {units[i]}".strip())
         print(f"| {k} | `{r[col['Kernel Name']][:38]}` | " + " | ".join(cells) + " |")
+    def to_bytes(val, unit):
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        return float(val) * mult.get(unit, 1)
+
+    if "--csv" in sys.argv:
+        open(sys.argv[sys.argv.index("--csv") + 1], "w").write(out)
+    if "--traffic-json" in sys.argv:
+        import json
+
+        r = rows[2]
+        rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
+        wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+        dur = r[col["gpu__time_duration.sum"]] + " " + units[col["gpu__time_duration.sum"]]
+        note = sys.argv[sys.argv.index("--note") + 1] if "--note" in sys.argv else ""
+        json.dump(dict(dram_bytes_per_launch=rd + wr, dram_bytes_read=rd, dram_bytes_write=wr, duration=dur, kernel=r[col["Kernel Name"]],
+                       source=sys.argv[1].split("/")[-1], note=note), open(sys.argv[sys.argv.index("--traffic-json") + 1], "w"), indent=1)
     if "--list" in sys.argv:
         for h in hdr:
             print(h)
