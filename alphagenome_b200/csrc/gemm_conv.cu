@@ -53,6 +53,7 @@ struct GemmKParams {
   AgGemmArgs g;
   int n_tile, m_tiles, n_tiles, total_tiles, kblocks;   // m_tiles counts (128 * CG)-row tiles
   int n_last;                                           // width of N tile n_tiles-1 (mixed-width tiling: k x n_tile + remainder)
+  int stream_res;                                       // residual rows bypass L1 (env AGB_EPI_STREAM=1; A/B timing only — measured slower)
   int a_bmask;                                          // 0 when A is shared by every batch (a_bstride == 0), else -1
   unsigned int* err;
 };
@@ -121,9 +122,9 @@ __device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool i
 }
 
 // Per-channel epilogue parameters are re-read by every tile: keep them in what little L1 the 226 KB of shared memory
-// leaves (evict_last), and let the residual rows — a pure stream, 64-128 KB per tile — bypass L1 (no_allocate).  ncu
-// (profiles/ncu_r02_summary.md): 39 % of the HBM-bound w1 GEMM's stall samples sat on the first use of pre_shift, an
-// L1 miss queued behind the residual stream that had evicted it.
+// leaves (evict_last).  ncu (profiles/ncu_r02_summary.md): 39 % of the HBM-bound w1 GEMM's stall samples sit on the first
+// FFMA after the staging read (long scoreboard).  Letting the residual rows bypass L1 (no_allocate, ldg4_stream) was
+// tried as the remedy and measured 1 % SLOWER (A/B on one box, AGB_EPI_STREAM=1): it stays off.
 __device__ __forceinline__ float4 ldg4_or(const float* p, float dflt) {
   if (p) {
     float4 v;
@@ -131,6 +132,15 @@ __device__ __forceinline__ float4 ldg4_or(const float* p, float dflt) {
     return v;
   }
   return make_float4(dflt, dflt, dflt, dflt);
+}
+// One float4 of a per-channel vector held by lane `src` of this warp (see the per-tile parameter registers below).
+__device__ __forceinline__ float4 shfl4(const float4& v, int src) {
+  float4 r;
+  r.x = __shfl_sync(0xffffffffu, v.x, src);
+  r.y = __shfl_sync(0xffffffffu, v.y, src);
+  r.z = __shfl_sync(0xffffffffu, v.z, src);
+  r.w = __shfl_sync(0xffffffffu, v.w, src);
+  return r;
 }
 __device__ __forceinline__ float4 ldg4_stream(const float* p) {
   float4 v;
@@ -313,6 +323,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const float* tB_t = (kActB && g.actB.shift) ? g.actB.shift + (long)b * g.actB.shift_bstride + n0 : nullptr;
       const float* sP_t = (has_actP && g.actP.scale) ? g.actP.scale + n0 : nullptr;
       const float* tP_t = (has_actP && g.actP.shift) ? g.actP.shift + (long)b * g.actP.shift_bstride + n0 : nullptr;
+      // Per-channel parameters of the whole tile, ONE float4 register per (scale, shift) pair and lane: this warp's
+      // chunks ch = slot + 4k (k = 0..3) cover 16 float4 positions idx = 4k + cg; lanes 0-15 hold the scale vector at
+      // position idx = lane, lanes 16-31 the shift vector at idx = lane - 16.  Loaded here, BEFORE the wait for the
+      // accumulator, and handed to the chunk loop by warp shuffles — the first version loaded them inside the loop
+      // right before their first use, where 39 % of the HBM-bound w1 GEMM's stall samples sat (ncu, long scoreboard).
+      float4 regPre, regA, regB, regP;
+      {
+        const int idx = lane & 15;
+        const int pcol = ((slot + 4 * (idx >> 2)) * kEpiCols) + 4 * (idx & 3);   // in-tile column of this lane's float4
+        const bool inb = pcol < (nt == p.n_tiles - 1 ? p.n_last : p.n_tile);
+        const bool hi = lane >= 16;
+        regPre = ldg4_or(inb ? (hi ? (pt_t ? pt_t + pcol : nullptr) : (ps_t ? ps_t + pcol : nullptr)) : nullptr, hi ? 0.0f : 1.0f);
+        if constexpr (kActA) regA = ldg4_or(inb ? (hi ? (tA_t ? tA_t + pcol : nullptr) : (sA_t ? sA_t + pcol : nullptr)) : nullptr, hi ? 0.0f : 1.0f);
+        if constexpr (kActB) regB = ldg4_or(inb ? (hi ? (tB_t ? tB_t + pcol : nullptr) : (sB_t ? sB_t + pcol : nullptr)) : nullptr, hi ? 0.0f : 1.0f);
+        if (has_actP) regP = ldg4_or(inb ? (hi ? (tP_t ? tP_t + pcol : nullptr) : (sP_t ? sP_t + pcol : nullptr)) : nullptr, hi ? 0.0f : 1.0f);
+      }
       const int res_cols = kRes ? g.res_ch - n0 : 0;   // residual applies to in-tile columns < res_cols
       const int rows_left = g.M - row_t;               // in-tile rows >= rows_left do not exist
 
@@ -331,7 +357,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             const int lr = lr_base + 2 * rsel + ((k & 1) ^ (rsel & 1)) + 16 * (k >> 1);
             rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (on && lr < rows_left)
-              rr[k] = ldg4_stream(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col));
+              rr[k] = p.stream_res ? ldg4_stream(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col))
+                                   : __ldg(reinterpret_cast<const float4*>(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col)));
           }
         }
         uint32_t r[16];
@@ -340,13 +367,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(st_wr + (((st_u0 + j) ^ st_x) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        // per-channel parameters (L1-resident after the first tile)
-        const float4 ps = ldg4_or(ps_t ? ps_t + col : nullptr, 1.0f);
-        const float4 pt = ldg4_or(pt_t ? pt_t + col : nullptr, 0.0f);
+        // per-channel parameters of this chunk: from the per-tile registers of lanes 4k + cg (scale) / 16 + 4k + cg (shift)
+        const int psrc = (((ch - slot) >> 2) << 2) + cg;
+        const float4 ps = shfl4(regPre, psrc), pt = shfl4(regPre, psrc + 16);
         float4 sA, tA, sB, tB, sP, tP;
-        if constexpr (kActA) { sA = ldg4_or(sA_t ? sA_t + col : nullptr, 1.0f); tA = ldg4_or(tA_t ? tA_t + col : nullptr, 0.0f); }
-        if constexpr (kActB) { sB = ldg4_or(sB_t ? sB_t + col : nullptr, 1.0f); tB = ldg4_or(tB_t ? tB_t + col : nullptr, 0.0f); }
-        if (has_actP) { sP = ldg4_or(sP_t ? sP_t + col : nullptr, 1.0f); tP = ldg4_or(tP_t ? tP_t + col : nullptr, 0.0f); }
+        if constexpr (kActA) { sA = shfl4(regA, psrc); tA = shfl4(regA, psrc + 16); }
+        if constexpr (kActB) { sB = shfl4(regB, psrc); tB = shfl4(regB, psrc + 16); }
+        if (has_actP) { sP = shfl4(regP, psrc); tP = shfl4(regP, psrc + 16); }
         __syncwarp();
 
 #pragma unroll
@@ -516,6 +543,14 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
   p.kblocks = (a.K + kBlockK - 1) / kBlockK;
   p.err = device_error_word(device);
+  {
+    static int v = -1;
+    if (v < 0) {
+      const char* e = getenv("AGB_EPI_STREAM");
+      v = (e && e[0] == '1') ? 1 : 0;   // measured: -1.0 % step time with the stream hint (each residual row of an upsampling
+    }                                   // epilogue is read twice, and L1 served the second read) -> off by default
+    p.stream_res = v;
+  }
 
   {
     const bool a_shared = a.batch > 1 && a.a_bstride == 0;   // one A for every batch (e.g. a weight as the row operand)
