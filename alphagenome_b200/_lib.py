@@ -8,8 +8,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libagb200.so"
+# AGB200_LIB: load another build of the library (A/B timing of kernel variants on one box); default = the in-tree build
+LIB_PATH = Path(os.environ["AGB200_LIB"]) if os.environ.get("AGB200_LIB") else _PKG / "libagb200.so"
 
 
 class AgEpiOut(C.Structure):
