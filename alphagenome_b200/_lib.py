@@ -159,6 +159,8 @@ EXPORTED = [
     "ag_bn_stats_fwd",
     "ag_bn_update_fwd",
     "ag_affine_act_fwd",
+    "ag_qkv_post_gather_fwd",
+    "ag_peer_push_fwd",
 ]
 
 _lib = None
@@ -201,6 +203,8 @@ def load() -> C.CDLL:
     lib.ag_pair_out_embed_fwd.argtypes = [P] * 6 + [I32] * 4 + [C.c_int, P]
     lib.ag_rmsnorm_act_fwd.argtypes = [P] * 5 + [I64, I64, I32, I32, C.c_int, P]
     lib.ag_splice_rope_fwd.argtypes = [P] * 6 + [I32] * 6 + [C.c_int, P]
+    lib.ag_qkv_post_gather_fwd.argtypes = [P, P, C.POINTER(C.c_void_p), I32, I64, I64] + [P] * 8 + [I32] * 5 + [C.c_int, P]
+    lib.ag_peer_push_fwd.argtypes = [P, C.POINTER(C.c_void_p), I32, I64, I64, C.c_int, P]
     lib.ag_bn_stats_fwd.argtypes = [P, P, I32, I32, I64, I32, I32, C.c_int, P]
     lib.ag_bn_update_fwd.argtypes = [P, C.c_double, P, P, C.c_float, C.c_float, P, P, P, P, I32, C.c_int, P]
     lib.ag_affine_act_fwd.argtypes = [C.POINTER(AgAffineArgs), C.c_int, P]

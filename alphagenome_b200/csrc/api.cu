@@ -266,6 +266,22 @@ int ag_splice_rope_fwd(const float* x, const float* scale, const float* offset, 
                             static_cast<cudaStream_t>(stream));
 }
 
+int ag_qkv_post_gather_fwd(const float* qkv, void* Q, void* const* kv_peers, int32_t world, int64_t n_all, int64_t row0,
+                           const float* cos_tab, const float* sin_tab, const float* q_w, const float* q_b, const float* k_w,
+                           const float* k_b, const float* v_w, const float* v_b, int32_t B, int32_t n, int32_t heads, int32_t d,
+                           int32_t dv, int device, void* stream) {
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  return launch_qkv_post_gather(qkv, Q, kv_peers, world, n_all, row0, cos_tab, sin_tab, q_w, q_b, k_w, k_b, v_w, v_b, B, n, heads, d, dv,
+                                device, static_cast<cudaStream_t>(stream));
+}
+
+int ag_peer_push_fwd(const void* src, void* const* peers, int32_t world, int64_t bytes, int64_t dst_offset, int device, void* stream) {
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  return launch_peer_push(src, peers, world, bytes, dst_offset, device, static_cast<cudaStream_t>(stream));
+}
+
 int ag_bn_stats_fwd(const float* x, double* sums, int32_t B, int32_t rows, int64_t bstride, int32_t ld, int32_t C, int device,
                     void* stream) {
   DeviceGuard guard(device);

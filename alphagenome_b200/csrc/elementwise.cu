@@ -121,6 +121,99 @@ __global__ void qkv_post_kernel(const float* __restrict__ qkv, __nv_bfloat16* __
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Sequence parallel: q/k/v LayerNorm + RoPE FUSED WITH THE K/V ALL-GATHER.  Every rank attends over the whole context
+// (AG:748), so each rank's K and V rows are needed by all ranks.  Instead of writing K/V locally and calling an
+// all-gather, the warp that finishes a K (V) row stores it straight into EVERY rank's gathered [B][n_all][d + dv]
+// buffer (peer-mapped symmetric memory: remote stores travel over NVLink / NVSwitch while the other warps are still
+// normalising).  Q stays local.  The consumers are ordered behind one cross-rank barrier by the caller.
+// ---------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+  __nv_bfloat16* p[8];
+};
+
+template <int PER_LANE>
+__device__ __forceinline__ void ln_rope_unit_peers(const float* __restrict__ src, const PeerPtrs& peers, int world, long elem_off,
+                                                   const float* __restrict__ w, const float* __restrict__ bvec,
+                                                   const float* __restrict__ cs, const float* __restrict__ sn, int lane, bool rope) {
+  float x[PER_LANE];
+  const int c0 = lane * PER_LANE;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i += 2) {
+    const float2 t = *reinterpret_cast<const float2*>(src + c0 + i);
+    x[i] = t.x;
+    x[i + 1] = t.y;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) s += x[i];
+  const float mean = warp_sum(s) / (32.0f * PER_LANE);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    x[i] -= mean;
+    v += x[i] * x[i];
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (32.0f * PER_LANE) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) x[i] = x[i] * rstd * __ldg(w + c0 + i) + __ldg(bvec + c0 + i);
+  if (rope) {
+#pragma unroll
+    for (int i = 0; i < PER_LANE; i += 2) {
+      const int f = (c0 + i) >> 1;
+      const float c = __ldg(cs + f), sgn = __ldg(sn + f);
+      const float a = x[i], b2 = x[i + 1];
+      x[i] = a * c - b2 * sgn;
+      x[i + 1] = b2 * c + a * sgn;
+    }
+  }
+  uint32_t pk[PER_LANE / 2];
+#pragma unroll
+  for (int i = 0; i < PER_LANE; i += 2) pk[i / 2] = pack2(x[i], x[i + 1]);
+  for (int r = 0; r < world; ++r) {
+    __nv_bfloat16* row = peers.p[r] + elem_off + c0;
+    if constexpr (PER_LANE == 4) {
+      *reinterpret_cast<uint2*>(row) = make_uint2(pk[0], pk[1]);      // K: the warp writes one contiguous 256 B row
+    } else {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(row);
+#pragma unroll
+      for (int i = 0; i < PER_LANE / 2; ++i) dst[i] = pk[i];
+    }
+  }
+}
+
+__global__ void qkv_post_gather_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ Q, PeerPtrs kv, int world,
+                                       long n_all, long row0, const float* __restrict__ cos_tab,
+                                       const float* __restrict__ sin_tab, const float* q_w, const float* q_b, const float* k_w,
+                                       const float* k_b, const float* v_w, const float* v_b, long tokens, int n, int heads) {
+  const int lane = threadIdx.x & 31;
+  const int units = heads + 2;
+  const long total = tokens * units;
+  const int C = heads * 128 + 128 + 192;
+  for (long wi = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; wi < total; wi += ((long)gridDim.x * blockDim.x) >> 5) {
+    const int u = (int)(wi % units);
+    const long tkn = wi / units;
+    const int pos = (int)(tkn % n);
+    const long bb = tkn / n;
+    const float* src = qkv + tkn * C;
+    const float* cs = cos_tab + (long)pos * 64;
+    const float* sn = sin_tab + (long)pos * 64;
+    const long grow = (bb * n_all + row0 + pos) * 320;          // row of [K | V] in a gathered buffer
+    if (u < heads) ln_rope_unit<4>(src + u * 128, Q + tkn * (heads * 128) + u * 128, q_w, q_b, cs, sn, lane, true);
+    else if (u == heads) ln_rope_unit_peers<4>(src + heads * 128, kv, world, grow, k_w, k_b, cs, sn, lane, true);
+    else ln_rope_unit_peers<6>(src + heads * 128 + 128, kv, world, grow + 128, v_w, v_b, cs, sn, lane, false);
+  }
+}
+
+// One-launch push all-gather over peer memory: `bytes` of src go to byte offset dst_off of every rank's buffer.
+__global__ void peer_push_kernel(const uint4* __restrict__ src, PeerPtrs peers, int world, long n16, long dst_off16) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n16 * world; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / n16);
+    const long j = i - r * n16;
+    reinterpret_cast<uint4*>(peers.p[r])[dst_off16 + j] = __ldg(src + j);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // bf16 transpose through a padded smem tile: out[b][c][r] = in[b][r][c]
 // ---------------------------------------------------------------------------------------------------
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C,
@@ -525,6 +618,37 @@ int launch_qkv_post(const float* qkv, void* Q, void* K, void* V, const float* co
       qkv, (__nv_bfloat16*)Q, (__nv_bfloat16*)K, (__nv_bfloat16*)V, cos_tab, sin_tab, q_w, q_b, k_w, k_b, v_w, v_b,
       (long)B * n, n, heads);
   return check_launch("ag_qkv_post_fwd");
+}
+
+int launch_qkv_post_gather(const float* qkv, void* Q, void* const* kv_peers, int world, long n_all, long row0, const float* cos_tab,
+                           const float* sin_tab, const float* q_w, const float* q_b, const float* k_w, const float* k_b,
+                           const float* v_w, const float* v_b, int B, int n, int heads, int d, int dv, int device, cudaStream_t st) {
+  if (d != 128 || dv != 192) return set_error("ag_qkv_post_gather_fwd: built for d=128, dv=192 (got %d, %d)", d, dv);
+  if (!qkv || !Q || !kv_peers || !cos_tab || !sin_tab) return set_error("ag_qkv_post_gather_fwd: null pointer");
+  if (world < 1 || world > 8) return set_error("ag_qkv_post_gather_fwd: world=%d must be in [1, 8]", world);
+  if (row0 < 0 || row0 + n > n_all) return set_error("ag_qkv_post_gather_fwd: rows [%ld, %ld) outside n_all=%ld", row0, row0 + n, n_all);
+  PeerPtrs kv;
+  for (int r = 0; r < 8; ++r) kv.p[r] = r < world ? static_cast<__nv_bfloat16*>(kv_peers[r]) : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!kv.p[r] || (reinterpret_cast<uintptr_t>(kv.p[r]) & 15)) return set_error("ag_qkv_post_gather_fwd: peer buffer %d is null or misaligned", r);
+  const long warps = (long)B * n * (heads + 2);
+  qkv_post_gather_kernel<<<grid_for(warps * 32, 256, device), 256, 0, st>>>(qkv, (__nv_bfloat16*)Q, kv, world, n_all, row0, cos_tab, sin_tab,
+                                                                           q_w, q_b, k_w, k_b, v_w, v_b, (long)B * n, n, heads);
+  return check_launch("ag_qkv_post_gather_fwd");
+}
+
+int launch_peer_push(const void* src, void* const* peers, int world, long bytes, long dst_offset, int device, cudaStream_t st) {
+  if (!src || !peers) return set_error("ag_peer_push_fwd: null pointer");
+  if (world < 1 || world > 8) return set_error("ag_peer_push_fwd: world=%d must be in [1, 8]", world);
+  if ((bytes & 15) || (dst_offset & 15) || bytes <= 0 || (reinterpret_cast<uintptr_t>(src) & 15))
+    return set_error("ag_peer_push_fwd: sizes, offsets and pointers must be multiples of 16 bytes");
+  PeerPtrs pp;
+  for (int r = 0; r < 8; ++r) pp.p[r] = r < world ? static_cast<__nv_bfloat16*>(peers[r]) : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!pp.p[r] || (reinterpret_cast<uintptr_t>(pp.p[r]) & 15)) return set_error("ag_peer_push_fwd: peer buffer %d is null or misaligned", r);
+  const long n16 = bytes / 16;
+  peer_push_kernel<<<grid_for(n16 * world, 256, device, 2), 256, 0, st>>>(static_cast<const uint4*>(src), pp, world, n16, dst_offset / 16);
+  return check_launch("ag_peer_push_fwd");
 }
 
 int launch_transpose_bf16(const void* in, void* out, int nb, int R, int C, long in_bs, int in_ld, long out_bs,

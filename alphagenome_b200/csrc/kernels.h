@@ -54,6 +54,10 @@ int launch_rmsnorm_act(const float* x, const float* w, const float* b, const flo
 int launch_splice_rope(const float* x, const float* scale, const float* offset, const float* cos_tab, const float* sin_tab,
                        void* out, int B, int P, int T, int Hd, int p_ld, int tab_per_site, int device, cudaStream_t st);
 
+int launch_qkv_post_gather(const float* qkv, void* Q, void* const* kv_peers, int world, long n_all, long row0, const float* cos_tab,
+                           const float* sin_tab, const float* q_w, const float* q_b, const float* k_w, const float* k_b,
+                           const float* v_w, const float* v_b, int B, int n, int heads, int d, int dv, int device, cudaStream_t st);
+int launch_peer_push(const void* src, void* const* peers, int world, long bytes, long dst_offset, int device, cudaStream_t st);
 int launch_bn_stats(const float* x, double* sums, int B, int rows, long bstride, int ld, int C, int device, cudaStream_t st);
 int launch_bn_update(const double* sums, double count, float* running_var, const float* gamma, float momentum, float eps,
                      float* scale_out, const float* fold_bias, const float* fold_beta, float* fold_shift_out, int C, int device,

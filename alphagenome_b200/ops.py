@@ -461,3 +461,29 @@ def affine_act(x, scale=None, shift=None, *, res=None, out_f32=None, out_bf16=No
         a.out_bf16, a.out_bf16_bstride, a.out_bf16_ld = o.data_ptr(), bst(o), o.stride(1)
     a.B, a.rows, a.C, a.act = B, rows, Cc, int(act)
     _lib.check(_lib.load().ag_affine_act_fwd(C.byref(a), _dev(x), _stream(x)))
+
+
+# ------------------------------------------------------------------------------------------------ sequence parallel, peer memory
+def _peer_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def qkv_post_gather(qkv, Q, kv_peer_ptrs, n_all: int, row0: int, cos_tab, sin_tab, qw, qb, kw, kb, vw, vb, heads: int, d: int, dv: int) -> None:
+    """ag_qkv_post_gather_fwd: qkv_post whose K / V rows go straight into every rank's gathered [B, n_all, d + dv] buffer
+    (kv_peer_ptrs: device pointers of the symmetric allocation, one per rank)."""
+    B, n, Ctot = qkv.shape
+    _require(Ctot == heads * d + d + dv, "qkv channel count mismatch")
+    for t, nm in ((qkv, "qkv"), (cos_tab, "cos"), (sin_tab, "sin"), (qw, "qw"), (qb, "qb"), (kw, "kw"), (kb, "kb"), (vw, "vw"), (vb, "vb")):
+        _f32(t, nm)
+    _require(cos_tab.shape[0] >= n and cos_tab.shape[1] == d // 2, "rope tables must be [>=n, d/2]")
+    _require(Q.dtype == torch.bfloat16 and Q.is_contiguous(), "Q must be contiguous bf16")
+    _lib.check(_lib.load().ag_qkv_post_gather_fwd(qkv.data_ptr(), Q.data_ptr(), _peer_array(kv_peer_ptrs), len(kv_peer_ptrs), n_all, row0,
+                                                  cos_tab.data_ptr(), sin_tab.data_ptr(), qw.data_ptr(), qb.data_ptr(), kw.data_ptr(), kb.data_ptr(),
+                                                  vw.data_ptr(), vb.data_ptr(), B, n, heads, d, dv, _dev(qkv), _stream(qkv)))
+
+
+def peer_push(src: torch.Tensor, peer_ptrs, dst_offset_bytes: int) -> None:
+    """ag_peer_push_fwd: src (contiguous) -> byte offset dst_offset_bytes of every rank's buffer."""
+    _require(src.is_cuda and src.is_contiguous(), "src must be a contiguous CUDA tensor")
+    _lib.check(_lib.load().ag_peer_push_fwd(src.data_ptr(), _peer_array(peer_ptrs), len(peer_ptrs), src.numel() * src.element_size(),
+                                            int(dst_offset_bytes), _dev(src), _stream(src)))

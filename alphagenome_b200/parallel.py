@@ -24,6 +24,7 @@ world_size 2).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -115,6 +116,19 @@ class SeqParallel:
         # NCCL moves device buffers directly over NVLink.  With the gloo backend (CPU tests; the 2-process
         # single-GPU parity test) device tensors are staged through host memory — test plumbing only.
         self._stage = dist.get_backend(group) == "gloo"
+        # Peer-memory path (NVLink / NVSwitch): gathers whose producer is one of our kernels are written by that kernel
+        # straight into every rank's symmetric buffer, followed by ONE cross-rank barrier per tower layer, instead of
+        # an NCCL all-gather per tensor.  Needs one GPU per rank and NCCL; AGB_SP_PEER=0 keeps the NCCL collectives.
+        self._symm = {}
+        self.peer = False
+        if not self._stage and self.world > 1 and self.world <= 8 and torch.cuda.is_available() and os.environ.get("AGB_SP_PEER", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+
+                self.peer = torch.cuda.device_count() >= self.world
+            except Exception:  # noqa: BLE001 — no symmetric-memory support in this torch build
+                self.peer = False
+        self.n_barriers = 0
 
     def _all_gather(self, out: torch.Tensor, x: torch.Tensor) -> None:
         if self._stage and x.is_cuda:
@@ -124,6 +138,26 @@ class SeqParallel:
         else:
             dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group)
         self.n_collectives += 1
+
+    # ------------------------------------------------------------------------------------------ peer memory
+    def symm_buffer(self, key, shape, dtype, device):
+        """A symmetric allocation (same shape on every rank, peer-mapped): returns (local tensor, handle).  Cached by
+        `key`; the first call is a collective (rendezvous), so every rank must ask for the same keys in the same order."""
+        ent = self._symm.get(key)
+        if ent is None:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            t = symm_mem.empty(*shape, dtype=dtype, device=device)
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            ent = (t, hdl, [int(p) for p in hdl.buffer_ptrs])
+            self._symm[key] = ent
+        return ent
+
+    def peer_barrier(self, hdl, channel: int = 0):
+        """All ranks' earlier stores into the symmetric buffers are visible to every rank's later kernels (stream-ordered,
+        device-side; a lost peer trips the timeout instead of hanging the GPU)."""
+        hdl.barrier(channel=channel, timeout_ms=20000)
+        self.n_barriers += 1
 
     class _Pending:
         """An all-gather in flight on NCCL's stream; wait() orders the current stream after it and returns the result."""

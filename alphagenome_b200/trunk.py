@@ -400,6 +400,11 @@ class TrunkEngine:
         xsg = torch.empty(2, B, Pl, D, device=single.device, dtype=torch.bfloat16)    # [0] normalised pooled rows, [1] their erf-GELU
         ops.pool_rmsnorm(single, sp["nw"], sp["nb"], xsg[0], xsg[1], sp["pool"])
         if plan is not None and plan.world > 1:
+            if self.sp.peer:
+                # one-launch push into every rank's symmetric [world, 2B, Pl, D] buffer; made visible by the layer's barrier
+                buf, hdl, ptrs = self.sp.symm_buffer(("rows", li & 2, B, Pl, D), (plan.world, 2 * B, Pl, D), torch.bfloat16, single.device)
+                ops.peer_push(xsg, ptrs, plan.rank * xsg.numel() * 2)
+                return ("peer", buf, hdl)
             return self.sp.gather_rows_async(xsg.view(2 * B, Pl, D))
         return xsg
 
@@ -417,7 +422,10 @@ class TrunkEngine:
         if pooled is None:
             pooled = self._pool_rows(P, li, single, plan)
         if plan is not None and plan.world > 1:
-            g = pooled.wait().view(2, B, plan.P, D)
+            if isinstance(pooled, tuple):     # peer path: [world, 2B, Pl, D], already behind the layer's barrier
+                g = pooled[1].view(plan.world, 2, B, Pl, D).permute(1, 2, 0, 3, 4).reshape(2, B, plan.P, D)
+            else:
+                g = pooled.wait().view(2, B, plan.P, D)
             xs, xg, Pn, i0 = g[0], g[1], plan.P, plan.row_off
         else:
             xs, xg, Pn, i0 = pooled[0], pooled[1], Pl, 0
@@ -504,15 +512,26 @@ class TrunkEngine:
             qkv = torch.empty(B, n, Hh * d + d + dv, **f32)
             ops.gemm(a, at["Wqkv"], out=qkv)
             Q = torch.empty(B, n, Hh * d, **bf)
-            K = torch.empty(B, n, d, **bf)
-            V = torch.empty(B, n, dv, **bf)
-            ops.qkv_post(qkv, Q, K, V, cos_t, sin_t, at["qw"], at["qb"], at["kw"], at["kb"], at["vw"], at["vb"], Hh, d, dv)
             kv_pending = None
-            if sharded:  # K/V of every rank (AG:748 attends over the whole context); Q and the bias rows stay local
-                kv_pending = self.sp.gather_rows_async(torch.cat((K, V), dim=-1))   # ONE all-gather per layer: [B, n_all, d + dv]
+            if sharded and self.sp.peer:
+                # K/V of every rank (AG:748 attends over the whole context): the LayerNorm + RoPE kernel stores this rank's
+                # K | V rows straight into every rank's gathered buffer over NVLink (fused compute + all-gather); one
+                # barrier per layer then covers them and the pooled rows pushed above.  Two buffers alternate between
+                # layers: a rank can only be writing layer l+2's rows after every rank has passed layer l+1's barrier,
+                # i.e. after every rank's layer-l attention has finished reading.
+                KV, hdl, ptrs = self.sp.symm_buffer(("kv", li & 1, B, n_all, d + dv), (B, n_all, d + dv), torch.bfloat16, dev)
+                ops.qkv_post_gather(qkv, Q, ptrs, n_all, plan.tok_off, cos_t, sin_t, at["qw"], at["qb"], at["kw"], at["kb"], at["vw"], at["vb"], Hh, d, dv)
+                self.sp.peer_barrier(hdl)
+                K, V = KV[..., :d], KV[..., d:]
+            else:
+                K = torch.empty(B, n, d, **bf)
+                V = torch.empty(B, n, dv, **bf)
+                ops.qkv_post(qkv, Q, K, V, cos_t, sin_t, at["qw"], at["qb"], at["kw"], at["kb"], at["vw"], at["vb"], Hh, d, dv)
+                if sharded:  # NCCL fallback: ONE all-gather per layer of [K | V], in flight while the pair block runs
+                    kv_pending = self.sp.gather_rows_async(torch.cat((K, V), dim=-1))
             if "s2p" in L:
                 pair = self._pair_block(P, li, single, pair, plan, pooled=pooled)
-            if sharded:
+            if kv_pending is not None:
                 KV = kv_pending.wait()
                 K, V = KV[..., :d], KV[..., d:]                         # strided views (TMA / transpose take a row stride)
             nk = _round_up(n_all, 8)

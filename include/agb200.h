@@ -212,6 +212,22 @@ int ag_add_embed_norm_fwd(const float* x, const float* emb, const float* scale, 
 int ag_pair_out_embed_fwd(const float* pair, const float* pairT, const float* w, const float* b, const float* emb,
                           float* out, int32_t B, int32_t rows, int32_t P, int32_t C, int device, void* stream);
 
+/* --- sequence parallel over NVLink peer memory (no reference counterpart: the reference has no sequence parallelism) --- */
+
+/* ag_qkv_post_fwd FUSED WITH THE K/V ALL-GATHER of a sequence-parallel rank (AG:748 attends over the whole context):
+ * Q [B][n][heads*d] stays local; the K and V rows of this rank's n tokens are stored, as [K | V] rows of width d + dv, at
+ * rows [row0, row0 + n) of EVERY rank's gathered buffer kv_peers[r] (bf16 [B][n_all][d + dv]; peer-mapped device
+ * pointers of a symmetric allocation, r < world <= 8; kv_peers itself is a HOST array) — remote stores over NVLink /
+ * NVSwitch issued by the warp that just finished the row.  The caller orders consumers behind a cross-rank barrier. */
+int ag_qkv_post_gather_fwd(const float* qkv, void* Q, void* const* kv_peers, int32_t world, int64_t n_all, int64_t row0,
+                           const float* cos_tab, const float* sin_tab, const float* q_w, const float* q_b, const float* k_w,
+                           const float* k_b, const float* v_w, const float* v_b, int32_t B, int32_t n, int32_t heads, int32_t d,
+                           int32_t dv, int device, void* stream);
+
+/* One-launch push all-gather: `bytes` at src are stored at byte offset dst_offset of every rank's buffer peers[r]
+ * (HOST array of peer-mapped device pointers); sizes / offsets / pointers multiples of 16 bytes. */
+int ag_peer_push_fwd(const void* src, void* const* peers, int32_t world, int64_t bytes, int64_t dst_offset, int device, void* stream);
+
 /* --- BatchRMSNorm with updating statistics (AG:324-361 with update_running_var, the reference's default; ---------
  * --- get_maybe_dist_var AG:276-300).  The frozen path is folded into ag_gemm_fwd's epilogue instead. ---------- */
 
