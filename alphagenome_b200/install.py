@@ -54,7 +54,8 @@ def _adapt(unet) -> None:
 
 def install(model):
     """Swap `model.get_embeds` (AG:1754-1778) for the B200 engine.  `model` is a reference `AlphaGenome` (or the
-    mirror in alphagenome_b200.model).  Inference only: BatchRMSNorm uses its frozen running variance."""
+    mirror in alphagenome_b200.model).  BatchRMSNorm behaves as the modules say: `update_running_var` true (the
+    reference's default) re-estimates the variance on every forward in the module's own buffer, false is the frozen path."""
     unet = model.transformer_unet
     _adapt(unet)
     for oe in (model.outembed_128bp, model.outembed_1bp):
