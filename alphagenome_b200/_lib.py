@@ -65,6 +65,15 @@ class AgGemmArgs(C.Structure):
         ("actA", AgEpiOut),
         ("actB", AgEpiOut),
         ("actP", AgEpiOut),
+        ("A2", C.c_void_p),
+        ("W2", C.c_void_p),
+        ("a2_bstride", C.c_int64),
+        ("a2_ld", C.c_int32),
+        ("a2_rows", C.c_int32),
+        ("a2_row0", C.c_int32),
+        ("w2_ld", C.c_int32),
+        ("K2", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 

@@ -53,6 +53,7 @@ struct AttnKParams {
   CUtensorMap tmV;   // (keys, dv, kv_heads, batch)
   AgAttnArgs a;
   int q_tiles, nblk;
+  int dbg;             // row_attention_kernel timing experiments (env AGB_ROWATTN_DBG, bring-up only; 0 in production)
   int tile_off;        // first tile of this launch (a call may be issued as a full-wave launch + a key-split tail launch)
   unsigned int* err;
 };
@@ -514,6 +515,404 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
   }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Persistent row attention (mode 1 as the trunk calls it: <= 512 keys, dv = 128, fp32 out + bias + residual + the pair
+// feed-forward's RMSNorm).  The kernel above runs one 128-query tile per CTA; a pair block at 1 Mbp is 2048 such tiles of
+// only 8 short steps each, i.e. 13.8 waves of CTAs whose launch, barrier / TMEM set-up, Q and K load latencies and
+// epilogue are all exposed (ncu r2: tensor pipe 17 %, MUFU 13 %, warps active 28 %; 0.47 ms per block in the step
+// against a ~0.08 ms HBM floor).  Here ONE CTA per SM walks tiles blockIdx.x, + gridDim.x, ... with every role running
+// ahead across tile boundaries:
+//   * TMA producer: the K ring (4 stages = all <= 4 key blocks of a tile, resident for both passes) is refilled for tile
+//     t+1 as tile t's pass-2 QK^T MMAs release the stages; V^T blocks stream through a 2-stage ring;
+//   * MMA issuer: tile t+1's pass-1 QK^T products are issued while the softmax warps are still in tile t's epilogue
+//     (Q is double-buffered in TMEM: 64 columns are free because dv = 128 leaves O at 128 instead of 192 columns);
+//   * softmax warps: Q rows of tile t+1 are requested at the start of tile t and stored to TMEM between its passes; the
+//     residual rows are requested before the last P.V drains (as above); O is handed back to the MMA warp (o_empty) as
+//     soon as it is in registers, before the stores and the RMSNorm.
+// Barrier phases are carried in running counters (steps per tile = 2 x key blocks is even, so the S ping-pong keeps
+// its parity across tiles).  Row max / row sum / sum of squares are exchanged through three separate smem arrays, which
+// makes one named barrier per exchange sufficient (the next write to an array is always behind two later barriers).
+// ----------------------------------------------------------------------------------------------------
+constexpr int kRowVBytes = 128 * kAttBN * 2;   // dv = 128: 32 KB per V^T block
+constexpr int kRowStgBytes = 4 * 32 * 128;    // epilogue staging: per 32-row group, 32 rows x 32 fp32 columns, swizzled
+constexpr int kRowSmem = kAttKStages * kAttKBytes + 2 * kRowVBytes + 2 * kAttXchBytes + kRowStgBytes + 256;   // 217,344 B
+constexpr uint32_t kTmemQ1 = 384;   // second Q buffer (tile parity 1); parity 0 uses kTmemQ
+
+__global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __grid_constant__ AttnKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const AgAttnArgs& a = p.a;
+  constexpr int dv = 128;
+
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kAttKStages * kAttKBytes;
+  float* xmax = reinterpret_cast<float*>(sV + 2 * kRowVBytes);   // [4][128] each
+  float* xsum = xmax + 4 * kAttBM;
+  uint8_t* stg_all = reinterpret_cast<uint8_t*>(xsum + 4 * kAttBM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + kRowStgBytes);
+  uint64_t* q_full = bars;         // [2]  Q rows of tile parity 0 / 1 are in TMEM (16 softmax warps arrive)
+  uint64_t* k_full = bars + 2;     // [4]
+  uint64_t* k_empty = bars + 6;    // [4]
+  uint64_t* v_full = bars + 10;    // [2]
+  uint64_t* v_empty = bars + 12;   // [2]
+  uint64_t* s_full = bars + 14;    // [2]
+  uint64_t* s_empty = bars + 16;   // [2]
+  uint64_t* p_full = bars + 18;    // [2 S stages][2 key halves]
+  uint64_t* o_full = bars + 22;    // [1]
+  uint64_t* o_empty = bars + 23;   // [1]  the epilogue has O in registers (16 softmax warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = p.q_tiles * a.heads * a.batch;
+  const int nblk = p.nblk;          // 1..4 key blocks, the same for every tile
+  const int np1 = (p.dbg & 2) ? 0 : nblk;   // pass-1 steps (dbg bit 1: timing without the row-max pass)
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) {
+      if (p.err) { p.err[0] = 0xDEAD0A12u; __threadfence_system(); }
+      __trap();
+    }
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], kAttSmxWarps);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], kAttSmxWarps);
+    }
+    for (int i = 0; i < kAttKStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], kAttSmxWarps / 2);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, kAttSmxWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + kTmemO;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t gv = 0;   // V^T blocks loaded so far
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int h = (tile / p.q_tiles) % a.heads;
+        const int b = tile / (p.q_tiles * a.heads);
+        const int hk = a.kv_heads == 1 ? 0 : h;
+        for (int j = 0; j < nblk; ++j) {
+          mbar_wait(&k_empty[j], (uint32_t)(it & 1) ^ 1u, 0x210u + j, p.err);   // released by the previous tile's pass-2 product
+          mbar_arrive_expect_tx(&k_full[j], kAttKBytes);
+          tma_load_4d(sK + j * kAttKBytes, &p.tmK, &k_full[j], 0, j * kAttBN, hk, b);
+          tma_load_4d(sK + j * kAttKBytes + kAttKBytes / 2, &p.tmK, &k_full[j], 64, j * kAttBN, hk, b);
+        }
+        for (int f = 0; f < nblk; ++f, ++gv) {
+          const int vs = gv & 1;
+          mbar_wait(&v_empty[vs], ((gv >> 1) & 1u) ^ 1u, 0x220u + vs, p.err);
+          mbar_arrive_expect_tx(&v_full[vs], kRowVBytes);
+          tma_load_4d(sV + vs * kRowVBytes, &p.tmV, &v_full[vs], f * kAttBN, 0, hk, b);
+          tma_load_4d(sV + vs * kRowVBytes + kRowVBytes / 2, &p.tmV, &v_full[vs], f * kAttBN + 64, 0, hk, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(kAttBM, kAttBN);
+      const uint32_t idesc_o = make_idesc_bf16(kAttBM, (uint32_t)dv);
+      const int nsteps = np1 + nblk;
+      uint32_t g = 0;    // QK^T products issued so far (S stage = g & 1)
+      uint32_t gv = 0;   // P.V products issued so far
+      uint32_t pc[2] = {0u, 0u};   // P tiles consumed per S stage
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const uint32_t tmem_Q = tmem_base + ((it & 1) ? kTmemQ1 : kTmemQ);
+        mbar_wait(&q_full[it & 1], (uint32_t)(it >> 1) & 1u, 0x200u + (it & 1), p.err);
+        tc_fence_after();
+        for (int s = 0; s <= nsteps; ++s) {
+          if (s < nsteps) {
+            const int st = g & 1;
+            const int j = s < np1 ? s : s - np1;   // key block = K stage
+            if (s < nblk) mbar_wait(&k_full[j], (uint32_t)(it & 1), 0x230u + j, p.err);   // pass 2 finds the tile resident
+            mbar_wait(&s_empty[st], ((g >> 1) & 1u) ^ 1u, 0x240u + st, p.err);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + j * kAttKBytes + (kk >> 2) * (kAttKBytes / 2)));
+              tc_mma_bf16_ts(tmem_S + (uint32_t)st * kAttBN, tmem_Q + (uint32_t)(8 * kk), dk + (uint64_t)(2 * (kk & 3)), idesc_s,
+                             kk > 0 ? 1u : 0u);
+            }
+            if (s >= np1) tc_commit(&k_empty[j]);   // the stage may take the next tile's key block
+            tc_commit(&s_full[st]);
+            ++g;
+          }
+          if (s >= 1 && (s - 1) >= np1) {
+            const int f = s - 1 - np1;
+            const int vs = gv & 1;
+            const int pst = (g - (s < nsteps ? 2u : 1u)) & 1;   // the S stage step s-1 used
+            mbar_wait(&v_full[vs], (gv >> 1) & 1u, 0x250u + vs, p.err);
+            if (f == 0) {   // O still holds the previous tile until its epilogue has it in registers
+              mbar_wait(o_empty, (uint32_t)(it & 1) ^ 1u, 0x280u, p.err);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              mbar_wait(&p_full[pst * 2 + hf], pc[pst] & 1u, 0x260u + pst * 2 + hf, p.err);
+              tc_fence_after();
+              const uint64_t dvv = make_sw128_kmajor_desc(smem_u32(sV + vs * kRowVBytes + hf * (kRowVBytes / 2)));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t pa = tmem_S + (uint32_t)pst * kAttBN + (uint32_t)(32 * (2 * hf + (k >> 1)) + 8 * (k & 1));
+                tc_mma_bf16_ts(tmem_O, pa, dvv + (uint64_t)(2 * k), idesc_o, (f > 0 || hf > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            ++pc[pst];
+            tc_commit(&v_empty[vs]);
+            ++gv;
+          }
+        }
+        tc_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------- softmax + epilogue
+    const int qd = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int hf = cq >> 1;
+    const int lrow = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    const float sc_plain = a.scale * LOG2E;
+    const int rr = lane >> 3, cg = lane & 7;   // epilogue layout: rows 8 cq + rr (+ 4) of the group, channels 4 cg .. 4 cg + 3 of a chunk
+    uint8_t* stg = stg_all + qd * (32 * 128);
+    // the four warps of a 32-row group (same qd) only ever exchange data with each other: one named barrier per group
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + qd) : "memory"); };
+
+    // Q rows of a tile: this thread's row, channels [32 cq, 32 cq + 32) = 16 packed TMEM columns
+    auto q_load = [&](int tile, uint32_t (&qr)[16]) {
+      const int qt = tile % p.q_tiles;
+      const int h = (tile / p.q_tiles) % a.heads;
+      const int b = tile / (p.q_tiles * a.heads);
+      const int row = qt * kAttBM + lrow;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) qr[j] = 0u;
+      if (row < a.n_q && !(p.dbg & 8)) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.Q) + (long)b * a.q_bstride +
+                                                          (long)h * a.q_hstride + (long)row * a.q_ld + 32 * cq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 v = __ldg(src + j);
+          qr[4 * j] = v.x; qr[4 * j + 1] = v.y; qr[4 * j + 2] = v.z; qr[4 * j + 3] = v.w;
+        }
+      }
+    };
+    auto q_publish = [&](int parity, const uint32_t (&qr)[16]) {
+      tmem_st_32x16(tmem_base + (parity ? kTmemQ1 : kTmemQ) + lane_off + (uint32_t)(16 * cq), qr);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full[parity]);
+    };
+    if ((int)blockIdx.x < total) {
+      uint32_t qr[16];
+      q_load(blockIdx.x, qr);
+      q_publish(0, qr);
+    }
+
+    uint32_t g = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int qt = tile % p.q_tiles;
+      const int h = (tile / p.q_tiles) % a.heads;
+      const int b = tile / (p.q_tiles * a.heads);
+      const int row = qt * kAttBM + lrow;
+      const int next = tile + gridDim.x;
+      uint32_t qn[16];
+      if (next < total) q_load(next, qn);   // in flight during pass 1
+
+      // ---- pass 1: exact row maximum ----
+      float rowmax = -INFINITY;
+      for (int s = 0; s < np1; ++s, ++g) {
+        const int st = g & 1;
+        const int key0 = s * kAttBN + cq * 32;
+        mbar_wait(&s_full[st], (g >> 1) & 1u, 0x270u + st, p.err);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_S + lane_off + (uint32_t)st * kAttBN + (uint32_t)cq * 32, r);
+        tmem_ld_wait();
+        if (key0 + 32 <= a.n_k) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rowmax = fmaxf(rowmax, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (key0 + j < a.n_k) rowmax = fmaxf(rowmax, __uint_as_float(r[j]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
+      }
+      xmax[cq * kAttBM + lrow] = rowmax;
+      group_sync();
+      rowmax = fmaxf(fmaxf(xmax[lrow], xmax[kAttBM + lrow]), fmaxf(xmax[2 * kAttBM + lrow], xmax[3 * kAttBM + lrow]));
+      const float mneg = np1 ? -rowmax * sc_plain : 0.0f;
+      // the other Q buffer was last read by the tile before this one, whose products all completed long ago
+      if (next < total) q_publish((it + 1) & 1, qn);
+
+      // ---- pass 2: p = exp(logit - max) -> P (bf16, over the S columns just read) ----
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < nblk; ++s, ++g) {
+        const int st = g & 1;
+        const int key0 = s * kAttBN + cq * 32;
+        mbar_wait(&s_full[st], (g >> 1) & 1u, 0x270u + st, p.err);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_S + lane_off + (uint32_t)st * kAttBN + (uint32_t)cq * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(s_addr, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = (p.dbg & 4) ? fmaf(__uint_as_float(r[j]), sc_plain, mneg) : ex2_approx(fmaf(__uint_as_float(r[j]), sc_plain, mneg));
+        if (key0 + 32 > a.n_k) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (key0 + j >= a.n_k) pv[j] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rsum[j & 3] += pv[j];
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(pv[2 * j], pv[2 * j + 1]);
+        tmem_st_32x16(s_addr, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&p_full[st * 2 + hf]);
+          mbar_arrive(&s_empty[st]);
+        }
+      }
+
+      // ---- epilogue: O / rowsum + to_v bias + residual (fp32), RMSNormWithBias of the finished row (bf16) ----
+      // TMEM hands a thread ONE ROW (rows are 512 B apart in global memory), so loading the residual and storing out /
+      // norm_out straight from that layout touches 32 different 128-byte lines per warp instruction, 16 bytes each:
+      // with it the launch takes 264 us, without any epilogue traffic 138 us (timing experiment, P = 512).  The four
+      // warps that share 32 rows therefore exchange the tile through a swizzled 4 KB staging buffer, 32 columns at a
+      // time: warp cq then owns rows 8 cq .. 8 cq + 7 of the group with lanes across the channels, so every global
+      // access is 4 rows x 128 contiguous bytes.
+      const int r0 = qt * kAttBM + qd * 32 + cq * 8 + rr;       // this lane's rows: r0 and r0 + 4
+      const long ob = (long)b * a.out_bstride + (long)h * a.out_hstride;
+      const bool ok0 = r0 < a.n_q && !(p.dbg & 1), ok1 = r0 + 4 < a.n_q && !(p.dbg & 1);
+      // y starts as the residual (requested now, in flight while the last P.V drains) and ends as the finished row
+      float y[32];      // [chunk][row 0: 4 channels | row 1: 4 channels]
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = 0.f;
+      if (a.res != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (ok0) asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y[8 * c]), "=f"(y[8 * c + 1]), "=f"(y[8 * c + 2]), "=f"(y[8 * c + 3])
+                                : "l"(a.res + ob + (long)r0 * a.out_ld + c * 32 + cg * 4));
+          if (ok1) asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y[8 * c + 4]), "=f"(y[8 * c + 5]), "=f"(y[8 * c + 6]), "=f"(y[8 * c + 7])
+                                : "l"(a.res + ob + (long)(r0 + 4) * a.out_ld + c * 32 + cg * 4));
+        }
+      }
+      xsum[cq * kAttBM + lrow] = (rsum[0] + rsum[1]) + (rsum[2] + rsum[3]);
+      group_sync();
+      const float inv = 1.0f / ((xsum[lrow] + xsum[kAttBM + lrow]) + (xsum[2 * kAttBM + lrow] + xsum[3 * kAttBM + lrow]));
+      mbar_wait(o_full, (uint32_t)(it & 1), 0x290u, p.err);
+      tc_fence_after();
+      float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[8];
+        tmem_ld_32x8(tmem_O + lane_off + (uint32_t)(c * 32 + cq * 8), r);
+        tmem_ld_wait();
+        if (c == 3) {                             // O is in registers: the next tile's P.V may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty);
+        }
+        if (c > 0) group_sync();                  // the previous chunk has been read by all four warps
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          *reinterpret_cast<float4*>(stg + lane * 128 + (((cq * 2 + u) ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(r[4 * u]) * inv, __uint_as_float(r[4 * u + 1]) * inv, __uint_as_float(r[4 * u + 2]) * inv,
+                          __uint_as_float(r[4 * u + 3]) * inv);
+        group_sync();
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.out_bias) bb = __ldg(reinterpret_cast<const float4*>(a.out_bias + c * 32 + cg * 4));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int gr = cq * 8 + rr + 4 * i;     // row inside the group
+          float4 v = *reinterpret_cast<const float4*>(stg + gr * 128 + ((cg ^ (gr & 7)) << 4));
+          v.x = (v.x + bb.x) + y[8 * c + 4 * i]; v.y = (v.y + bb.y) + y[8 * c + 4 * i + 1];     // same order as the
+          v.z = (v.z + bb.z) + y[8 * c + 4 * i + 2]; v.w = (v.w + bb.w) + y[8 * c + 4 * i + 3]; // one-tile kernel: bit-identical
+          const bool ok = i ? ok1 : ok0;
+          if (ok) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + ob + (long)(r0 + 4 * i) * a.out_ld + c * 32 + cg * 4) = v;
+          }
+          const float sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          if (i) ss1 += sq; else ss0 += sq;
+          y[8 * c + 4 * i] = v.x; y[8 * c + 4 * i + 1] = v.y; y[8 * c + 4 * i + 2] = v.z; y[8 * c + 4 * i + 3] = v.w;
+        }
+      }
+      // a row's 128 channels sit in the 8 lanes that share rr: three butterfly steps complete the sums of squares
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+      }
+      const float rinv0 = rsqrtf(ss0 * (1.0f / 128.0f) + 1e-5f), rinv1 = rsqrtf(ss1 * (1.0f / 128.0f) + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.norm_w + c * 32 + cg * 4));
+        const float4 nb4 = __ldg(reinterpret_cast<const float4*>(a.norm_b + c * 32 + cg * 4));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (!(i ? ok1 : ok0)) continue;
+          const float ri = i ? rinv1 : rinv0;
+          const float* yy = y + 8 * c + 4 * i;
+          uint2 pk;
+          pk.x = pack_bf16x2(fmaf(yy[0] * ri, w.x, nb4.x), fmaf(yy[1] * ri, w.y, nb4.y));
+          pk.y = pack_bf16x2(fmaf(yy[2] * ri, w.z, nb4.z), fmaf(yy[3] * ri, w.w, nb4.w));
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.norm_out) + ob + (long)(r0 + 4 * i) * a.out_ld + c * 32 + cg * 4) = pk;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// env AGB_ROWATTN=0 keeps the one-tile-per-CTA kernel for the row attention (A/B timing)
+static bool rowattn_persistent() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_ROWATTN");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // exponentials per 8 evaluated by polynomial in mode 0 (env AGB_ATTN_POLY = 0, 2, 4, 5 or 6; default 2, the fastest
 // measured on B200: 0.369 ms per 8192-token layer against 0.393 (0), 0.375 (4), 0.407 (6))
 static int attn_poly_of8() {
@@ -563,6 +962,35 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
     uint64_t str[3] = {(uint64_t)a.v_ld * 2, (uint64_t)a.v_hstride * 2, (uint64_t)a.v_bstride * 2};
     uint32_t box[4] = {64, (uint32_t)a.dv, 1, 1};
     if (int rc = make_tensor_map_bf16(&p.tmV, a.Vt, 4, dims, str, box)) return rc;
+  }
+  if (a.mode == 1 && a.norm_out != nullptr && a.dv == 128 && p.nblk <= kAttKStages && rowattn_persistent()) {
+    const long tiles = (long)p.q_tiles * a.heads * a.batch;
+    if (tiles > 1073741823L) return set_error("ag_attention_fwd: grid too large");
+    {
+      const char* e = getenv("AGB_ROWATTN_DBG");
+      p.dbg = e ? atoi(e) : 0;
+    }
+    static thread_local unsigned char attr_done[64];
+    if (!attr_done[device]) {
+      cudaError_t e = cudaFuncSetAttribute(row_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
+      if (e != cudaSuccess) return set_error("ag_attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_done[device] = 1;
+    }
+    const int sms = sm_count(device);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms), 1, 1);   // persistent: one CTA per SM
+    cfg.blockDim = dim3(kAttThreads, 1, 1);
+    cfg.dynamicSmemBytes = kRowSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, row_attention_kernel, p);
+    if (le != cudaSuccess) return set_error("ag_attention_fwd: launch failed: %s", cudaGetErrorString(le));
+    return check_launch("ag_attention_fwd");
   }
   // key split: two CTAs per tile when that shortens the schedule (waves x blocks per CTA; the DSMEM combine costs about
   // 6 blocks' worth: measured 0.371 -> 0.385 ms at 512 tiles x 64 blocks, 0.098 -> 0.063 ms at 64 tiles x 64 blocks).

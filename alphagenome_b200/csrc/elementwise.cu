@@ -315,6 +315,101 @@ __global__ void __launch_bounds__(256) pair_bias_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// to_attn_bias on the tensor core (the default path).  The projection is a [cells x 128] . [128 x 8] product per layer:
+// as plain FMAs + a transposing butterfly it cost ~260 issue slots per cell and lane and ran at 0.16 of the HBM rate
+// (ncu r1: ALU-bound).  Here a warp owns 16 consecutive cells and feeds them to mma.sync.m16n8k16 (bf16 in, fp32
+// accumulate): N = 8 heads is exactly one n-tile, so the whole projection of a layer is 8 MMAs per 16 cells, and the
+// result fragment (thread = 2 cells x 2 heads) stores as full 32-byte sectors.  (tcgen05 would need M = 128 x N >= 16
+// tiles staged through shared memory and TMEM for a product whose tensor time is ~1 % of its HBM time; the legacy warp
+// MMA keeps the operand in the registers the GELU just produced.)
+//
+// The MMA sums over k, so the k order is free: lane (g = lane >> 2, t = lane & 3) loads channels 16s + 4t .. + 3 of
+// cells g and g + 8 with ONE 128-bit load each per k-step s and assigns them to k-slots {2t, 2t+1, 2t+8, 2t+9}; the W
+// fragment uses the same map.  The operand is bf16 like every other tensor-core operand of the path, so erf-GELU is
+// evaluated in the one-MUFU form 0.5 x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))), coefficients fitted to erf-GELU
+// (max |error| 2.5e-5 before tanh.approx's 2^-11, below the bf16 rounding of the operand).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf_tanh(float x) {
+  const float t = fminf(x * x, 64.0f);            // beyond |x| = 8 the argument of tanh is >= 13.8: exactly +-1
+  float q = fmaf(t, -3.51516786e-4f, 3.70056460e-2f);
+  q = fmaf(t, q, 7.97507884e-1f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(x * q), h);
+}
+
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int SETS>
+__global__ void __launch_bounds__(256, 2) pair_bias_mma_kernel(const float* __restrict__ pair, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, const float* __restrict__ W,
+                                                               float* __restrict__ bias, long groups, long per_b, long set_stride) {
+  __shared__ float4 s_sc[SETS][32], s_sh[SETS][32];
+  if (threadIdx.x < SETS * 32) {
+    const int s = threadIdx.x >> 5, i = threadIdx.x & 31;
+    s_sc[s][i] = __ldg(reinterpret_cast<const float4*>(scale + s * 128) + i);
+    s_sh[s][i] = __ldg(reinterpret_cast<const float4*>(shift + s * 128) + i);
+  }
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t bw[SETS][8][2];   // W fragments of head g: k-step s holds channels 16s + 4t .. + 3
+#pragma unroll
+  for (int s = 0; s < SETS; ++s)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W + (s * 8 + g) * 128 + 16 * k) + t);
+      bw[s][k][0] = pack2(w.x, w.y);
+      bw[s][k][1] = pack2(w.z, w.w);
+    }
+  __syncthreads();
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long grp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; grp < groups; grp += nwarps) {
+    const long cell0 = grp * 16;
+    const float4* p0 = reinterpret_cast<const float4*>(pair + (cell0 + g) * 128) + t;   // cell g; cell g + 8 is 256 float4 on
+    float acc[SETS][4];
+#pragma unroll
+    for (int s = 0; s < SETS; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 xa[4], xb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xa[j] = __ldg(p0 + 4 * (half * 4 + j));
+        xb[j] = __ldg(p0 + 256 + 4 * (half * 4 + j));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = half * 4 + j;
+#pragma unroll
+        for (int s = 0; s < SETS; ++s) {
+          const float4 sc = s_sc[s][4 * k + t], sh = s_sh[s][4 * k + t];
+          const uint32_t a0 = pack2(gelu_erf_tanh(fmaf(xa[j].x, sc.x, sh.x)), gelu_erf_tanh(fmaf(xa[j].y, sc.y, sh.y)));
+          const uint32_t a2 = pack2(gelu_erf_tanh(fmaf(xa[j].z, sc.z, sh.z)), gelu_erf_tanh(fmaf(xa[j].w, sc.w, sh.w)));
+          const uint32_t a1 = pack2(gelu_erf_tanh(fmaf(xb[j].x, sc.x, sh.x)), gelu_erf_tanh(fmaf(xb[j].y, sc.y, sh.y)));
+          const uint32_t a3 = pack2(gelu_erf_tanh(fmaf(xb[j].z, sc.z, sh.z)), gelu_erf_tanh(fmaf(xb[j].w, sc.w, sh.w)));
+          mma_m16n8k16_bf16(acc[s], a0, a1, a2, a3, bw[s][k][0], bw[s][k][1]);
+        }
+      }
+    }
+    // result fragment: acc[.][0..1] = cell g, heads 2t, 2t+1; acc[.][2..3] = cell g + 8.  A store instruction writes, for
+    // each of 4 heads, 8 consecutive cells = one full 32-byte sector.
+    const long b = cell0 / per_b;
+    const long ij = cell0 - b * per_b;
+#pragma unroll
+    for (int s = 0; s < SETS; ++s) {
+      float* d0 = bias + s * set_stride + (b * 8 + 2 * t) * per_b + ij + g;
+      d0[0] = acc[s][0];
+      d0[per_b] = acc[s][1];
+      d0[8] = acc[s][2];
+      d0[per_b + 8] = acc[s][3];
+    }
+  }
+}
+
 // cells that do not fill a group of 8 (or unaligned shapes): one warp per cell, plain reduction
 __global__ void pair_bias_tail_kernel(const float* __restrict__ pair, const float* __restrict__ scale,
                                       const float* __restrict__ shift, const float* __restrict__ W, float* __restrict__ bias,
@@ -667,7 +762,20 @@ int launch_pair_bias(const float* pair, const float* scale, const float* shift, 
   if (!pair || !scale || !shift || !W || !bias) return set_error("ag_pair_bias_fwd: null pointer");
   const long per_b = (long)rows * cols;
   const long cells = (long)B * per_b;
-  // fast path: groups of 8 consecutive cells inside one batch element, 16-byte aligned output rows
+  // tensor-core path: groups of 16 consecutive cells inside one batch element (AGB_PAIR_BIAS_MMA=0: the fp32 FMA kernels)
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    const char* e = getenv("AGB_PAIR_BIAS_MMA");
+    use_mma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_mma && heads == 8 && per_b % 16 == 0 && (reinterpret_cast<uintptr_t>(pair) & 15) == 0) {
+    const long groups16 = cells / 16;
+    const unsigned grid = grid_for(groups16 * 32, 256, device, 2);
+    if (sets == 2) pair_bias_mma_kernel<2><<<grid, 256, 0, st>>>(pair, scale, shift, W, bias, groups16, per_b, set_stride);
+    else pair_bias_mma_kernel<1><<<grid, 256, 0, st>>>(pair, scale, shift, W, bias, groups16, per_b, set_stride);
+    return check_launch("ag_pair_bias_fwd");
+  }
+  // fp32 path: groups of 8 consecutive cells inside one batch element, 16-byte aligned output rows
   const bool fast = heads == 8 && per_b % 8 == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (set_stride % 4) == 0;
   const long groups = fast ? cells / 8 : 0;
   if (groups > 0) {

@@ -50,9 +50,11 @@ struct GemmKParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
   CUtensorMap tmB2;                                     // W box of the LAST N tile (n_last wide); == tmB when uniform
+  CUtensorMap tmA2, tmW2, tmW2l;                        // optional second operand pair (AgGemmArgs.A2 / W2); tmW2l = last N tile
   AgGemmArgs g;
   int n_tile, m_tiles, n_tiles, total_tiles, kblocks;   // m_tiles counts (128 * CG)-row tiles
   int n_last;                                           // width of N tile n_tiles-1 (mixed-width tiling: k x n_tile + remainder)
+  int kblocks2;                                         // 64-deep K blocks of the second operand pair (0 = none)
   int stream_res;                                       // residual rows bypass L1 (env AGB_EPI_STREAM=1; A/B timing only — measured slower)
   int a_bmask;                                          // 0 when A is shared by every batch (a_bstride == 0), else -1
   unsigned int* err;
@@ -177,6 +179,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmB2);
+    if (p.kblocks2) {
+      tma_prefetch_desc(&p.tmA2);
+      tma_prefetch_desc(&p.tmW2);
+      tma_prefetch_desc(&p.tmW2l);
+    }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
   pdl_launch_dependents();   // the next kernel may be scheduled as our CTAs retire ...
   pdl_wait();                // ... and we read nothing from global memory before the previous kernel has completed
 
-  const int iters = g.taps * p.kblocks;
+  const int iters = g.taps * p.kblocks + p.kblocks2;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -237,6 +244,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+        }
+        // second operand pair: same boxes from its own tensor maps, accumulated into the same tile
+        const CUtensorMap* tmW2 = last_n ? &p.tmW2l : &p.tmW2;
+        const int row2 = g.a2_row0 + (mt * CG + (int)crank) * kBlockM;
+        for (int kb = 0; kb < p.kblocks2; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 0x10u + stage, p.err);
+          if constexpr (CG == 2) {
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (kABytes + b_bytes));
+            tma_load_3d_cg2(sA + stage * kABytes, &p.tmA2, &full_bar[stage], kb * kBlockK, row2, b);
+            tma_load_3d_cg2(sB + stage * kBStage, tmW2, &full_bar[stage], kb * kBlockK, wrow0, 0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_bytes);
+            tma_load_3d(sA + stage * kABytes, &p.tmA2, &full_bar[stage], kb * kBlockK, row2, b);
+            tma_load_3d(sB + stage * kBStage, tmW2, &full_bar[stage], kb * kBlockK, wrow0, 0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -530,6 +553,13 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   }
   if ((reinterpret_cast<uintptr_t>(a.pre_scale) | reinterpret_cast<uintptr_t>(a.pre_shift)) & 15)
     return set_error("ag_gemm_fwd: pre_scale/pre_shift must be 16-byte aligned");
+  if ((a.A2 == nullptr) != (a.W2 == nullptr)) return set_error("ag_gemm_fwd: A2 and W2 must be given together");
+  if (a.A2) {
+    if (a.w_batched || a.w_rows) return set_error("ag_gemm_fwd: the second operand pair needs a shared, unpadded W");
+    if (a.K2 < 8 || a.K2 % 8 || a.a2_ld % 8 || a.w2_ld % 8 || a.a2_bstride % 8 || a.a2_rows < 1)
+      return set_error("ag_gemm_fwd: K2, a2_ld, w2_ld, a2_bstride must be multiples of 8 and a2_rows >= 1");
+    if ((reinterpret_cast<uintptr_t>(a.A2) | reinterpret_cast<uintptr_t>(a.W2)) & 15) return set_error("ag_gemm_fwd: A2/W2 must be 16-byte aligned");
+  }
 
   GemmKParams p;
   memset(&p, 0, sizeof(p));
@@ -568,6 +598,23 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
     if (int rc = make_tensor_map_bf16(&p.tmB, a.W, 3, dims, strides, box)) return rc;
     box[1] = (uint32_t)(p.n_last / cg);
     if (int rc = make_tensor_map_bf16(&p.tmB2, a.W, 3, dims, strides, box)) return rc;
+  }
+  if (a.A2) {
+    p.kblocks2 = (a.K2 + kBlockK - 1) / kBlockK;
+    {
+      uint64_t dims[3] = {(uint64_t)a.K2, (uint64_t)a.a2_rows, (uint64_t)a.batch};
+      uint64_t strides[2] = {(uint64_t)a.a2_ld * 2, (uint64_t)(a.batch > 1 ? a.a2_bstride : (int64_t)a.a2_ld * a.a2_rows) * 2};
+      uint32_t box[3] = {kBlockK, kBlockM, 1};
+      if (int rc = make_tensor_map_bf16(&p.tmA2, a.A2, 3, dims, strides, box)) return rc;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)a.K2, (uint64_t)a.N, 1};
+      uint64_t strides[2] = {(uint64_t)a.w2_ld * 2, (uint64_t)a.w2_ld * a.N * 2};
+      uint32_t box[3] = {kBlockK, (uint32_t)(p.n_tile / cg), 1};
+      if (int rc = make_tensor_map_bf16(&p.tmW2, a.W2, 3, dims, strides, box)) return rc;
+      box[1] = (uint32_t)(p.n_last / cg);
+      if (int rc = make_tensor_map_bf16(&p.tmW2l, a.W2, 3, dims, strides, box)) return rc;
+    }
   }
 
   const int flags = (a.res ? F_RES : 0) | (a.out ? F_OUT : 0) | (a.actA.ptr ? F_ACTA : 0) | (a.actB.ptr ? F_ACTB : 0) |

@@ -98,10 +98,13 @@ def gemm(
     pool: Optional[torch.Tensor] = None,
     actP: Optional[Act] = None,
     cta_group: int = 0,
+    A2: Optional[torch.Tensor] = None,
+    W2: Optional[torch.Tensor] = None,
 ) -> None:
     """ag_gemm_fwd: conv1d (taps = W.shape[0]) / linear / batched matmul with the fused epilogue of agb200.h.
 
     A: bf16 [batch, a_rows, K];  W: bf16 [taps, N, K] (shared) or [batch, N, K] (w_batched).
+    A2 / W2: optional second operand pair, bf16 [batch, M, K2] / [N, K2], accumulated into the same tile.
     """
     lib = _lib.load()
     A = _as3(A)
@@ -176,6 +179,17 @@ def gemm(
     _fill_act(g.actA, actA, batch, M, N)
     _fill_act(g.actB, actB, batch, M, N)
     _fill_act(g.actP, actP, batch, M // 2, N)
+    if A2 is not None or W2 is not None:
+        _require(A2 is not None and W2 is not None, "A2 and W2 must be given together")
+        A2 = _as3(A2)
+        W2 = _as3(W2)
+        _require(A2.is_cuda and A2.dtype == torch.bfloat16 and W2.dtype == torch.bfloat16, "A2 and W2 must be CUDA bf16 tensors")
+        _require(A2.shape[0] == batch and A2.shape[1] >= M and W2.shape[0] == 1 and W2.shape[1] == N and W2.shape[2] == A2.shape[2],
+                 f"second operand pair: A2 {tuple(A2.shape)} W2 {tuple(W2.shape)} vs batch {batch}, M {M}, N {N}")
+        g.A2, g.W2 = A2.data_ptr(), W2.data_ptr()
+        g.a2_bstride = A2.stride(0) if batch > 1 else A2.stride(1) * A2.shape[1]
+        g.a2_ld, g.a2_rows, g.a2_row0 = A2.stride(1), A2.shape[1], 0
+        g.w2_ld, g.K2 = W2.stride(1), A2.shape[2]
     if PROFILE_GEMM is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -193,6 +207,8 @@ def gemm(
         if pool is not None:
             nbytes += batch * (M // 2) * N * 4
         nbytes += _out_bytes(actA, M) + _out_bytes(actB, M) + _out_bytes(actP, M // 2)
+        if A2 is not None:   # its 2*M*N*K2 products are a recomputation, not algorithmic work: bytes counted, FLOPs not
+            nbytes += batch * M * A2.shape[2] * 2 + W2.numel() * 2
         PROFILE_GEMM.append((e0, e1, 2.0 * batch * M * (w_rows or N) * K * taps, float(nbytes)))
         return
     _lib.check(lib.ag_gemm_fwd(C.byref(g), A.device.index or 0, _stream(A)))

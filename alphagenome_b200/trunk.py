@@ -144,6 +144,7 @@ class TrunkEngine:
         w15[:, : width * nb] = de.conv.weight.detach().to(device).permute(0, 2, 1).reshape(C0, width * nb)
         P["embed"] = dict(W=w15.to(torch.bfloat16).unsqueeze(0).contiguous(), b=vec(de.conv.bias), width=width, n_base=nb, K=k_emb)
         P["pointwise"] = convblock(de.pointwise)
+        P["pointwise"]["b_embed"] = (P["pointwise"]["b"] + P["embed"]["b"]).contiguous()   # both biases, for the fused residual
         P["downs"] = [dict(conv=convblock(d.conv), conv_out=convblock(d.conv_out)) for d in unet.downs]
         P["ups"] = [dict(conv=convblock(u.conv), unet_conv=convblock(u.unet_conv), conv_out=convblock(u.conv_out),
                          scale=vec(u.residual_scale)) for u in unet.ups]
@@ -352,10 +353,15 @@ class TrunkEngine:
         X = torch.empty(B, L, e["K"], **bf)
         ops.onehot_im2col(seq, X, e["width"], e["n_base"])
         pw = P["pointwise"]
-        x0 = torch.empty(B, L, C0, **f32)
         a0 = torch.empty(B, L, C0, **bf)
+        # x0 = conv15(one_hot) (AG:1177) is needed twice: normalised + activated as pointwise's operand (a0), and as the
+        # residual of x0 + pointwise(x0) (AG:1178).  The residual is re-derived on the tensor core — the K = 64 im2col
+        # product rides along as a second operand pair of the width-5 GEMM (+1.7 % MMA work), both biases summed —
+        # so at 1 Mbp the 3.2 GB fp32 x0 is neither written nor read back.  A pointwise norm that re-estimates its
+        # variance needs x0's statistics, hence x0 itself: that (default-constructed, updating) case keeps the plain form.
+        fuse_x0 = self._updating(pw["s"]) is None
+        x0 = None if fuse_x0 else torch.empty(B, L, C0, **f32)
         self._gemm(X, e["W"], pre_shift=e["b"], out=x0, actA=Act(a0, pw["s"], pw["t"], ACT_GELU1702))
-        del X
         ups = P["ups"]
         skips = [None] * (n_down + 1)  # skips[j] feeds ups[j]
         un = ups[n_down]["unet_conv"]
@@ -363,9 +369,13 @@ class TrunkEngine:
         x = torch.empty(B, L // 2, C0, **f32)
         a = torch.empty(B, L // 2, C0, **bf)
         d0 = P["downs"][0]["conv"]
-        self._gemm(a0, pw["W"], pre_shift=pw["b"], res=x0, actA=Act(skips[n_down], un["s"], un["t"], ACT_GELU1702),
-                 pool=x, actP=Act(a, d0["s"], d0["t"], ACT_GELU1702))
-        del x0, a0
+        if fuse_x0:
+            self._gemm(a0, pw["W"], pre_shift=pw["b_embed"], A2=X, W2=e["W"], actA=Act(skips[n_down], un["s"], un["t"], ACT_GELU1702),
+                       pool=x, actP=Act(a, d0["s"], d0["t"], ACT_GELU1702))
+        else:
+            self._gemm(a0, pw["W"], pre_shift=pw["b"], res=x0, actA=Act(skips[n_down], un["s"], un["t"], ACT_GELU1702),
+                       pool=x, actP=Act(a, d0["s"], d0["t"], ACT_GELU1702))
+        del x0, a0, X
         self._note("embed.pooled", x)
         length = L // 2
         for i, d in enumerate(P["downs"]):

@@ -64,6 +64,7 @@ typedef struct AgEpiOut {
  * AG:868-869, OutputEmbedding.double_features/skip_proj AG:1207-1208).
  *
  *   acc[b, r, n] = sum_{t<taps} sum_{k<K} A[b, r + t - taps/2, k] * W[z(b,t), n, k]        (fp32 accumulate)
+ *   (+ an optional second operand pair A2 . W2^T accumulated into acc, see the end of the struct)
  *   v = acc * pre_scale[n] + pre_shift[n];  if relu: v = max(v, 0)
  *   if res && n < res_ch: v += res[b, r >> res_shift, n]
  *   if post_scale: v *= *post_scale
@@ -108,6 +109,17 @@ typedef struct AgGemmArgs {
   float* pool;        /* fp32 [batch][M/2][N] or NULL */
   int64_t pool_bstride;
   AgEpiOut actA, actB, actP;
+  /* Optional SECOND operand pair accumulated into the same tile before the epilogue (A2 == NULL: none):
+   *   acc[b, r, n] += sum_{k<K2} A2[b, r, k] * W2[n, k]          (one tap; rows outside [0, a2_rows) read as zero)
+   * DNAEmbed (AG:1177-1178) uses it to add the width-15 convolution  x0 = conv(one_hot)  — a K2 = 64 im2col product —
+   * to pointwise(x0)'s accumulator on the tensor core, so the 1 bp fp32 x0 is neither written nor re-read as a residual. */
+  const void* A2;     /* bf16 [batch][a2_rows][K2], addressed like A (buffer row r + a2_row0) */
+  const void* W2;     /* bf16 [N][K2] shared by every batch */
+  int64_t a2_bstride;
+  int32_t a2_ld, a2_rows, a2_row0;
+  int32_t w2_ld;      /* elements between the N rows of W2 (multiple of 8) */
+  int32_t K2;         /* multiple of 8 */
+  int32_t reserved2;
 } AgGemmArgs;
 
 int ag_gemm_fwd(const AgGemmArgs* args, int device, void* stream);

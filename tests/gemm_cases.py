@@ -39,7 +39,7 @@ def ref_acc(A, W, M, a_row0, w_batched):
     return acc
 
 
-def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogue="plain", seed=0, strided=False, cta_group=0, a_shared=False):
+def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogue="plain", seed=0, strided=False, cta_group=0, a_shared=False, K2=0):
     """Returns dict(name, ok, max_err, details...). Tolerance: fp32-accumulate of bf16 products, so the only
     error is summation order -> 2e-3 relative to the output scale is generous and still catches any
     descriptor/layout bug (those give O(1) errors)."""
@@ -61,6 +61,13 @@ def run_case(name, *, batch, M, K, N, taps=1, a_row0=0, w_batched=False, epilogu
 
     res = {}
     kw = {}
+    if K2:
+        # second operand pair accumulated into the same tile (DNAEmbed: the one-hot im2col product rides along with
+        # the width-5 conv); the A2 buffer holds exactly the M output rows
+        A2 = (torch.randn(batch, M, K2, generator=gen) * 0.5).to(dev).bfloat16()
+        W2 = (torch.randn(1, N, K2, generator=gen) / math.sqrt(K2)).to(dev).bfloat16()
+        acc = acc + A2.double() @ W2[0].double().T
+        kw.update(A2=A2, W2=W2)
     checks = []
     f32 = dict(dtype=torch.float32, device=dev)
     if epilogue == "plain":
@@ -154,4 +161,9 @@ CASES = [
     dict(name="mixed_n272", batch=1, M=260, K=64, N=272),
     dict(name="mixed_n832_batched", batch=3, M=200, K=128, N=832, w_batched=True),
     dict(name="shared_a_batched_w", batch=6, M=128, K=128, N=48, w_batched=True, a_shared=True, epilogue="relu_bf16"),
+    # second operand pair (AgGemmArgs.A2 / W2): the DNAEmbed shape (conv5 768 -> 768 + a K2 = 64 im2col product, every
+    # epilogue output), a ragged M with a K2 tail block, and a mixed-width N with two batches
+    dict(name="second_pair_embed_shape", batch=1, M=4096, K=768, N=768, taps=5, epilogue="full", K2=64),
+    dict(name="second_pair_ragged_k2tail", batch=2, M=300, K=128, N=192, taps=5, K2=72),
+    dict(name="second_pair_mixed_n1152", batch=2, M=640, K=256, N=1152, epilogue="relu_bf16", K2=128),
 ]

@@ -73,8 +73,10 @@ def test_attention_key_split_matches_unsplit(monkeypatch):
     assert (O_s.float() - O_full[:, :nq].float()).abs().max().item() <= 2 ** -7 * O_full.float().abs().max().item()
 
 
-@pytest.mark.parametrize("B,P", [(1, 4), (2, 24), (1, 136), (1, 1)])
+@pytest.mark.parametrize("B,P", [(1, 4), (2, 24), (1, 136), (1, 1), (1, 300)])
 def test_attention_pair_rows(B, P):
+    """The call without norm_out runs the one-tile-per-CTA kernel, the call with it the persistent row-attention kernel
+    (P = 136: two tiles per CTA and 2 key blocks; P = 300: ~6 tiles per CTA, 3 key blocks, ragged last tile and block)."""
     D = 128
     x = g(B, P, P, 2 * D, seed=5, scale=1.5).bfloat16()   # q | k
     v = g(B, P, P, D, seed=6).bfloat16()
@@ -152,11 +154,11 @@ def test_transpose_bf16():
     assert torch.all(out[:, :, 70:] == 0)
 
 
-@pytest.mark.parametrize("B,rows,cols", [(2, 9, 9), (1, 8, 24), (2, 16, 64)])
+@pytest.mark.parametrize("B,rows,cols", [(2, 9, 9), (1, 8, 24), (2, 16, 64), (1, 5, 8)])
 @pytest.mark.parametrize("sets", [1, 2])
 def test_pair_bias_projection(B, rows, cols, sets):
-    """One and two parameter sets (two attention layers sharing the pair tensor); shapes that take the 8-cell fast
-    path (rows*cols % 8 == 0), the per-cell tail path (9x9) and a row shard (rows < cols)."""
+    """One and two parameter sets (two attention layers sharing the pair tensor); shapes that take the 16-cell tensor-core
+    path (rows*cols % 16 == 0), the per-cell fp32 tail path (9x9) and a row shard (rows < cols)."""
     pair = g(B, rows, cols, 128, seed=2, scale=3.0)
     c = lambda t: t.to(DEV).contiguous()
     S, T, W, want = [], [], [], []
@@ -167,14 +169,17 @@ def test_pair_bias_projection(B, rows, cols, sets):
         want.append(O.attention_bias(sd, "", pair).reshape(B, 8, rows, cols))
         s_, t_ = O.batch_rms_affine(sd, "to_attn_bias.0.")
         S.append(s_), T.append(t_), W.append(sd["to_attn_bias.2.weight"])
+    # rows*cols % 16 == 0 runs on the tensor core (bf16 operands like every other contraction of the path, one-MUFU
+    # erf-GELU): 4e-3 of the output scale; the fp32 FMA kernels that take every other shape stay at 1e-5
+    tol = 4e-3 if (rows * cols) % 16 == 0 else 1e-5
     if sets == 1:
         out = torch.full((B, 8, rows, cols), float("nan"), device=DEV)
         ops.pair_bias(c(pair), c(S[0]), c(T[0]), c(W[0]), out)
-        assert rel_err(out, want[0]) < 1e-5
+        assert rel_err(out, want[0]) < tol
     else:
         out = torch.full((2, B, 8, rows, cols), float("nan"), device=DEV)
         ops.pair_bias(c(pair), c(torch.stack(S)), c(torch.stack(T)), c(torch.stack(W)), out)
-        assert rel_err(out[0], want[0]) < 1e-5 and rel_err(out[1], want[1]) < 1e-5
+        assert rel_err(out[0], want[0]) < tol and rel_err(out[1], want[1]) < tol
 
 
 def test_pool_rmsnorm():

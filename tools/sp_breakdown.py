@@ -42,6 +42,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--length", type=int, default=1_048_576)
     ap.add_argument("--replays", type=int, default=5)
+    ap.add_argument("--out", default=None, help="output file name under gpurun_out/ (default sp_breakdown_N<world>.json)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -108,7 +109,7 @@ def main():
                    categories={k: dict(us_per_step=v[0] / R, launches_per_step=v[1] / R) for k, v in sorted(per_cat.items(), key=lambda kv: -kv[1][0])},
                    top_kernels={k: dict(us_per_step=v[0] / R, launches_per_step=v[1] / R) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])[:25]})
         (ROOT / "gpurun_out").mkdir(exist_ok=True)
-        (ROOT / "gpurun_out" / f"sp_breakdown_N{world}.json").write_text(json.dumps(out, indent=1))
+        (ROOT / "gpurun_out" / (args.out or f"sp_breakdown_N{world}.json")).write_text(json.dumps(out, indent=1))
         print("SP_BREAKDOWN " + json.dumps({k: out[k] for k in ("world", "ms_per_step_events", "span_us_per_step_profiled", "kernel_us_per_step", "idle_us_per_step", "categories")}))
     torch.cuda.synchronize()
     sys.stdout.flush()
