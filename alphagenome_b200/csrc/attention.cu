@@ -25,6 +25,7 @@
 // TMEM (512 columns): S ping-pong 2 x 128 | O 192 | Q 64.  P(s) aliases S(s): warp cq overwrites the first 16 of
 // its own 32 S columns, so no cross-warp hazard exists; S(s+2) cannot be overwritten before PV(s) has read P(s)
 // because tcgen05.mma executes in issue order.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -54,6 +55,10 @@ struct AttnKParams {
   AgAttnArgs a;
   int q_tiles, nblk;
   int dbg;             // row_attention_kernel timing experiments (env AGB_ROWATTN_DBG, bring-up only; 0 in production)
+  // row_attention_kernel work units: unit ids [0, rows_full) are whole rows (all q tiles, K loaded once); ids from rows_full
+  // on cut the remaining rows into upr units of u_tail q tiles each.  CTA c takes ids c, c + gridDim.x, ...
+  int rows_full, u_tail, upr, total_units;
+  unsigned long long* trace;   // AGB_TRACE builds only
   int tile_off;        // first tile of this launch (a call may be issued as a full-wave launch + a key-split tail launch)
   unsigned int* err;
 };
@@ -534,6 +539,16 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
 // makes one named barrier per exchange sufficient (the next write to an array is always behind two later barriers).
 // ----------------------------------------------------------------------------------------------------
 constexpr int kRowVBytes = 128 * kAttBN * 2;   // dv = 128: 32 KB per V^T block
+// Bring-up timeline (only in a -DAGB_TRACE build, python -m alphagenome_b200.csrc.build --trace): CTA 0's TMA thread, MMA
+// thread and one softmax thread stamp (tag, SM clock) pairs into a global buffer that AGB_ROWATTN_TRACE=<file> dumps.
+#ifdef AGB_TRACE
+#define ROW_TRACE(role, tag)                                                                                      \
+  do {                                                                                                            \
+    if (p.trace && blockIdx.x == 0 && trc < 2040) p.trace[(role) * 2048 + trc++] = ((unsigned long long)(tag) << 48) | (unsigned long long)(clock64() & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#else
+#define ROW_TRACE(role, tag) do {} while (0)
+#endif
 constexpr int kRowStgBytes = 4 * 32 * 128;    // epilogue staging: per 32-row group, 32 rows x 32 fp32 columns, swizzled
 constexpr int kRowSmem = kAttKStages * kAttKBytes + 2 * kRowVBytes + 2 * kAttXchBytes + kRowStgBytes + 256;   // 217,344 B
 constexpr uint32_t kTmemQ1 = 384;   // second Q buffer (tile parity 1); parity 0 uses kTmemQ
@@ -563,9 +578,16 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total = p.q_tiles * a.heads * a.batch;
   const int nblk = p.nblk;          // 1..4 key blocks, the same for every tile
   const int np1 = (p.dbg & 2) ? 0 : nblk;   // pass-1 steps (dbg bit 1: timing without the row-max pass)
+  // unit id -> (row = b * heads + h, q tiles [qt0, qt1))
+  auto decode = [&](int u, int& bh, int& qt0, int& qt1) {
+    if (u < p.rows_full) { bh = u; qt0 = 0; qt1 = p.q_tiles; return; }
+    const int t = u - p.rows_full;
+    bh = p.rows_full + t / p.upr;
+    qt0 = (t % p.upr) * p.u_tail;
+    qt1 = qt0 + p.u_tail < p.q_tiles ? qt0 + p.u_tail : p.q_tiles;
+  };
 
   if (warp == 0 && lane == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -607,23 +629,31 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
     // ---------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t gv = 0;   // V^T blocks loaded so far
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const int h = (tile / p.q_tiles) % a.heads;
-        const int b = tile / (p.q_tiles * a.heads);
+      int iu = 0;
+      int trc = 0; (void)trc;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++iu) {
+        int bh, qt0, qt1;
+        decode(u, bh, qt0, qt1);
+        const int h = bh % a.heads;
+        const int b = bh / a.heads;
         const int hk = a.kv_heads == 1 ? 0 : h;
+        // K: once per unit, resident for both passes of every q tile of the unit
         for (int j = 0; j < nblk; ++j) {
-          mbar_wait(&k_empty[j], (uint32_t)(it & 1) ^ 1u, 0x210u + j, p.err);   // released by the previous tile's pass-2 product
+          mbar_wait(&k_empty[j], (uint32_t)(iu & 1) ^ 1u, 0x210u + j, p.err);   // released by the previous unit's last pass-2 product
+          ROW_TRACE(0, 0x10 + j);
           mbar_arrive_expect_tx(&k_full[j], kAttKBytes);
           tma_load_4d(sK + j * kAttKBytes, &p.tmK, &k_full[j], 0, j * kAttBN, hk, b);
           tma_load_4d(sK + j * kAttKBytes + kAttKBytes / 2, &p.tmK, &k_full[j], 64, j * kAttBN, hk, b);
         }
-        for (int f = 0; f < nblk; ++f, ++gv) {
-          const int vs = gv & 1;
-          mbar_wait(&v_empty[vs], ((gv >> 1) & 1u) ^ 1u, 0x220u + vs, p.err);
-          mbar_arrive_expect_tx(&v_full[vs], kRowVBytes);
-          tma_load_4d(sV + vs * kRowVBytes, &p.tmV, &v_full[vs], f * kAttBN, 0, hk, b);
-          tma_load_4d(sV + vs * kRowVBytes + kRowVBytes / 2, &p.tmV, &v_full[vs], f * kAttBN + 64, 0, hk, b);
+        for (int qt = qt0; qt < qt1; ++qt) {
+          for (int f = 0; f < nblk; ++f, ++gv) {
+            const int vs = gv & 1;
+            mbar_wait(&v_empty[vs], ((gv >> 1) & 1u) ^ 1u, 0x220u + vs, p.err);
+            ROW_TRACE(0, 0x20 + f);
+            mbar_arrive_expect_tx(&v_full[vs], kRowVBytes);
+            tma_load_4d(sV + vs * kRowVBytes, &p.tmV, &v_full[vs], f * kAttBN, 0, hk, b);
+            tma_load_4d(sV + vs * kRowVBytes + kRowVBytes / 2, &p.tmV, &v_full[vs], f * kAttBN + 64, 0, hk, b);
+          }
         }
       }
     }
@@ -637,25 +667,33 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
       uint32_t g = 0;    // QK^T products issued so far (S stage = g & 1)
       uint32_t gv = 0;   // P.V products issued so far
       uint32_t pc[2] = {0u, 0u};   // P tiles consumed per S stage
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      int it = 0, iu = 0;
+      int trc = 0; (void)trc;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++iu) {
+        int bh, qt0, qt1;
+        decode(u, bh, qt0, qt1);
+      for (int qt = qt0; qt < qt1; ++qt, ++it) {
+        const bool first = qt == qt0, last = qt == qt1 - 1;
         const uint32_t tmem_Q = tmem_base + ((it & 1) ? kTmemQ1 : kTmemQ);
+        ROW_TRACE(1, 0x01);
         mbar_wait(&q_full[it & 1], (uint32_t)(it >> 1) & 1u, 0x200u + (it & 1), p.err);
         tc_fence_after();
+        ROW_TRACE(1, 0x02);
         for (int s = 0; s <= nsteps; ++s) {
           if (s < nsteps) {
             const int st = g & 1;
             const int j = s < np1 ? s : s - np1;   // key block = K stage
-            if (s < nblk) mbar_wait(&k_full[j], (uint32_t)(it & 1), 0x230u + j, p.err);   // pass 2 finds the tile resident
+            if (first && s < nblk) mbar_wait(&k_full[j], (uint32_t)(iu & 1), 0x230u + j, p.err);   // later products find the block resident
             mbar_wait(&s_empty[st], ((g >> 1) & 1u) ^ 1u, 0x240u + st, p.err);
             tc_fence_after();
+            ROW_TRACE(1, 0x10 + s);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + j * kAttKBytes + (kk >> 2) * (kAttKBytes / 2)));
               tc_mma_bf16_ts(tmem_S + (uint32_t)st * kAttBN, tmem_Q + (uint32_t)(8 * kk), dk + (uint64_t)(2 * (kk & 3)), idesc_s,
                              kk > 0 ? 1u : 0u);
             }
-            if (s >= np1) tc_commit(&k_empty[j]);   // the stage may take the next tile's key block
+            if (last && s >= np1) tc_commit(&k_empty[j]);   // the stage may take the next unit's key block
             tc_commit(&s_full[st]);
             ++g;
           }
@@ -679,12 +717,14 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
                 tc_mma_bf16_ts(tmem_O, pa, dvv + (uint64_t)(2 * k), idesc_o, (f > 0 || hf > 0 || k > 0) ? 1u : 0u);
               }
             }
+            ROW_TRACE(1, 0x20 + f);
             ++pc[pst];
             tc_commit(&v_empty[vs]);
             ++gv;
           }
         }
         tc_commit(o_full);
+      }
       }
     }
     __syncwarp();
@@ -703,10 +743,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + qd) : "memory"); };
 
     // Q rows of a tile: this thread's row, channels [32 cq, 32 cq + 32) = 16 packed TMEM columns
-    auto q_load = [&](int tile, uint32_t (&qr)[16]) {
-      const int qt = tile % p.q_tiles;
-      const int h = (tile / p.q_tiles) % a.heads;
-      const int b = tile / (p.q_tiles * a.heads);
+    auto q_load = [&](int bh, int qt, uint32_t (&qr)[16]) {
+      const int h = bh % a.heads;
+      const int b = bh / a.heads;
       const int row = qt * kAttBM + lrow;
 #pragma unroll
       for (int j = 0; j < 16; ++j) qr[j] = 0u;
@@ -727,22 +766,34 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_full[parity]);
     };
-    if ((int)blockIdx.x < total) {
+    if ((int)blockIdx.x < p.total_units) {
+      int bh, qt0, qt1;
+      decode(blockIdx.x, bh, qt0, qt1);
       uint32_t qr[16];
-      q_load(blockIdx.x, qr);
+      q_load(bh, qt0, qr);
       q_publish(0, qr);
     }
 
     uint32_t g = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int qt = tile % p.q_tiles;
-      const int h = (tile / p.q_tiles) % a.heads;
-      const int b = tile / (p.q_tiles * a.heads);
-      const int row = qt * kAttBM + lrow;
-      const int next = tile + gridDim.x;
+    int trc = (warp == 2 && lane == 0) ? 0 : 4096; (void)trc;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      int bh, qt0, qt1;
+      decode(u, bh, qt0, qt1);
+      const int h = bh % a.heads;
+      const int b = bh / a.heads;
+    for (int qt = qt0; qt < qt1; ++qt, ++it) {
+      // the tile after this one: the next q tile of the unit, or the first of this CTA's next unit
+      int nbh = bh, nqt = qt + 1;
+      bool has_next = nqt < qt1;
+      if (!has_next && u + (int)gridDim.x < p.total_units) {
+        int e;
+        decode(u + gridDim.x, nbh, nqt, e);
+        has_next = true;
+      }
+      ROW_TRACE(2, 0x01);
       uint32_t qn[16];
-      if (next < total) q_load(next, qn);   // in flight during pass 1
+      if (has_next) q_load(nbh, nqt, qn);   // in flight during pass 1
 
       // ---- pass 1: exact row maximum ----
       float rowmax = -INFINITY;
@@ -751,6 +802,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
         const int key0 = s * kAttBN + cq * 32;
         mbar_wait(&s_full[st], (g >> 1) & 1u, 0x270u + st, p.err);
         tc_fence_after();
+        ROW_TRACE(2, 0x10 + s);
         uint32_t r[32];
         tmem_ld_32x32(tmem_S + lane_off + (uint32_t)st * kAttBN + (uint32_t)cq * 32, r);
         tmem_ld_wait();
@@ -766,12 +818,15 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
       }
+      ROW_TRACE(2, 0x02);
       xmax[cq * kAttBM + lrow] = rowmax;
       group_sync();
+      ROW_TRACE(2, 0x03);
       rowmax = fmaxf(fmaxf(xmax[lrow], xmax[kAttBM + lrow]), fmaxf(xmax[2 * kAttBM + lrow], xmax[3 * kAttBM + lrow]));
       const float mneg = np1 ? -rowmax * sc_plain : 0.0f;
       // the other Q buffer was last read by the tile before this one, whose products all completed long ago
-      if (next < total) q_publish((it + 1) & 1, qn);
+      if (has_next) q_publish((it + 1) & 1, qn);
+      ROW_TRACE(2, 0x04);
 
       // ---- pass 2: p = exp(logit - max) -> P (bf16, over the S columns just read) ----
       float rsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -780,6 +835,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
         const int key0 = s * kAttBN + cq * 32;
         mbar_wait(&s_full[st], (g >> 1) & 1u, 0x270u + st, p.err);
         tc_fence_after();
+        ROW_TRACE(2, 0x20 + s);
         const uint32_t s_addr = tmem_S + lane_off + (uint32_t)st * kAttBN + (uint32_t)cq * 32;
         uint32_t r[32];
         tmem_ld_32x32(s_addr, r);
@@ -805,6 +861,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
           mbar_arrive(&p_full[st * 2 + hf]);
           mbar_arrive(&s_empty[st]);
         }
+        ROW_TRACE(2, 0x30 + s);
       }
 
       // ---- epilogue: O / rowsum + to_v bias + residual (fp32), RMSNormWithBias of the finished row (bf16) ----
@@ -833,8 +890,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
       xsum[cq * kAttBM + lrow] = (rsum[0] + rsum[1]) + (rsum[2] + rsum[3]);
       group_sync();
       const float inv = 1.0f / ((xsum[lrow] + xsum[kAttBM + lrow]) + (xsum[2 * kAttBM + lrow] + xsum[3 * kAttBM + lrow]));
+      ROW_TRACE(2, 0x05);
       mbar_wait(o_full, (uint32_t)(it & 1), 0x290u, p.err);
       tc_fence_after();
+      ROW_TRACE(2, 0x06);
       float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -876,6 +935,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
         ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
         ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
       }
+      ROW_TRACE(2, 0x07);
       const float rinv0 = rsqrtf(ss0 * (1.0f / 128.0f) + 1e-5f), rinv1 = rsqrtf(ss1 * (1.0f / 128.0f) + 1e-5f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -892,6 +952,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
           *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.norm_out) + ob + (long)(r0 + 4 * i) * a.out_ld + c * 32 + cg * 4) = pk;
         }
       }
+    }
     }
     tc_fence_before();
   }
@@ -977,9 +1038,32 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
       attr_done[device] = 1;
     }
     const int sms = sm_count(device);
+    // Work units.  A CTA that keeps a row's K resident across all its q tiles reads K once instead of q_tiles times (the
+    // kernel is L2->SM bound: K + V^T of a row are 256 KB, 1 MB per row when every q tile fetches both), but whole rows
+    // quantise badly (512 rows on 148 SMs = 3.46 rows each), so only the first floor(rows / G) * G rows are whole-row
+    // units and the rest are cut into units of u_tail q tiles, u_tail chosen for the shortest schedule (ties: larger).
+    const int rows = a.heads * a.batch;
+    const int G = tiles < sms ? (int)tiles : sms;
+    p.rows_full = (rows / G) * G;
+    const int tail = rows - p.rows_full;
+    p.u_tail = p.q_tiles;
+    if (tail > 0) {
+      long best = -1;
+      for (int u = p.q_tiles; u >= 1; --u) {
+        const long units = (long)tail * ((p.q_tiles + u - 1) / u);
+        const long cost = ((units + G - 1) / G) * u;
+        if (best < 0 || cost < best) { best = cost; p.u_tail = u; }
+      }
+    }
+    {
+      const char* e = getenv("AGB_ROWATTN_UNITS");   // 0: every q tile its own unit (K reloaded per tile)
+      if (e && e[0] == '0') { p.rows_full = 0; p.u_tail = 1; }
+    }
+    p.upr = (p.q_tiles + p.u_tail - 1) / p.u_tail;
+    p.total_units = p.rows_full + (rows - p.rows_full) * p.upr;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms), 1, 1);   // persistent: one CTA per SM
+    cfg.gridDim = dim3((unsigned)(p.total_units < G ? p.total_units : G), 1, 1);   // persistent: one CTA per SM
     cfg.blockDim = dim3(kAttThreads, 1, 1);
     cfg.dynamicSmemBytes = kRowSmem;
     cfg.stream = stream;
@@ -988,8 +1072,29 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+#ifdef AGB_TRACE
+    const char* trace_path = getenv("AGB_ROWATTN_TRACE");
+    if (trace_path) {
+      cudaMalloc(&p.trace, 3 * 2048 * sizeof(unsigned long long));
+      cudaMemsetAsync(p.trace, 0, 3 * 2048 * sizeof(unsigned long long), stream);
+    }
+#endif
     cudaError_t le = cudaLaunchKernelEx(&cfg, row_attention_kernel, p);
     if (le != cudaSuccess) return set_error("ag_attention_fwd: launch failed: %s", cudaGetErrorString(le));
+#ifdef AGB_TRACE
+    if (trace_path) {
+      static unsigned long long host[3 * 2048];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost);
+      cudaFree(p.trace);
+      if (FILE* f = fopen(trace_path, "w")) {   // the last launch wins
+        for (int r = 0; r < 3; ++r)
+          for (int i = 0; i < 2048 && host[r * 2048 + i]; ++i)
+            fprintf(f, "%d %llx %llu\n", r, host[r * 2048 + i] >> 48, host[r * 2048 + i] & 0xFFFFFFFFFFFFull);
+        fclose(f);
+      }
+    }
+#endif
     return check_launch("ag_attention_fwd");
   }
   // key split: two CTAs per tile when that shortens the schedule (waves x blocks per CTA; the DSMEM combine costs about

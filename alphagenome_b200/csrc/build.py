@@ -38,7 +38,10 @@ def _digest(paths: list[Path]) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> Path:
+    """trace=True: a separate libagb200_trace.so compiled with -DAGB_TRACE (bring-up timelines; load it with AGB200_LIB)."""
+    if trace:
+        return _build_variant("trace", ["-DAGB_TRACE"])
     srcs = sources()
     deps = srcs + sorted(HERE.glob("*.cuh")) + sorted(HERE.glob("*.h")) + [REPO / "include" / "agb200.h"]
     stamp = OBJ_DIR / "stamp.txt"
@@ -69,6 +72,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return OUT
 
 
+def _build_variant(tag: str, flags: list[str]) -> Path:
+    out = PKG / f"libagb200_{tag}.so"
+    odir = OBJ_DIR / tag
+    odir.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = odir / (src.stem + ".o")
+        r = subprocess.run([NVCC, *ARCH_FLAGS, *COMMON, *flags, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        objs.append(obj)
+    r = subprocess.run([NVCC, *ARCH_FLAGS, "-shared", "-o", str(out), *map(str, objs), "-Xlinker", "--exclude-libs,ALL"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv)
     print(p)
