@@ -54,10 +54,6 @@ struct AttnKParams {
   CUtensorMap tmV;   // (keys, dv, kv_heads, batch)
   AgAttnArgs a;
   int q_tiles, nblk;
-  int dbg;             // row_attention_kernel timing experiments (env AGB_ROWATTN_DBG, bring-up only; 0 in production)
-  // row_attention_kernel work units: unit ids [0, rows_full) are whole rows (all q tiles, K loaded once); ids from rows_full
-  // on cut the remaining rows into upr units of u_tail q tiles each.  CTA c takes ids c, c + gridDim.x, ...
-  int rows_full, u_tail, upr, total_units;
   unsigned long long* trace;   // AGB_TRACE builds only
   int tile_off;        // first tile of this launch (a call may be issued as a full-wave launch + a key-split tail launch)
   unsigned int* err;
@@ -521,24 +517,29 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Persistent row attention (mode 1 as the trunk calls it: <= 512 keys, dv = 128, fp32 out + bias + residual + the pair
-// feed-forward's RMSNorm).  The kernel above runs one 128-query tile per CTA; a pair block at 1 Mbp is 2048 such tiles of
-// only 8 short steps each, i.e. 13.8 waves of CTAs whose launch, barrier / TMEM set-up, Q and K load latencies and
-// epilogue are all exposed (ncu r2: tensor pipe 17 %, MUFU 13 %, warps active 28 %; 0.47 ms per block in the step
-// against a ~0.08 ms HBM floor).  Here ONE CTA per SM walks tiles blockIdx.x, + gridDim.x, ... with every role running
-// ahead across tile boundaries:
-//   * TMA producer: the K ring (4 stages = all <= 4 key blocks of a tile, resident for both passes) is refilled for tile
-//     t+1 as tile t's pass-2 QK^T MMAs release the stages; V^T blocks stream through a 2-stage ring;
-//   * MMA issuer: tile t+1's pass-1 QK^T products are issued while the softmax warps are still in tile t's epilogue
-//     (Q is double-buffered in TMEM: 64 columns are free because dv = 128 leaves O at 128 instead of 192 columns);
-//   * softmax warps: Q rows of tile t+1 are requested at the start of tile t and stored to TMEM between its passes; the
-//     residual rows are requested before the last P.V drains (as above); O is handed back to the MMA warp (o_empty) as
-//     soon as it is in registers, before the stores and the RMSNorm.
-// Barrier phases are carried in running counters (steps per tile = 2 x key blocks is even, so the S ping-pong keeps
-// its parity across tiles).  Row max / row sum / sum of squares are exchanged through three separate smem arrays, which
-// makes one named barrier per exchange sufficient (the next write to an array is always behind two later barriers).
+// Persistent row attention (mode 1 as the trunk calls it: dv = 128, fp32 out + bias + residual + the pair feed-forward's
+// RMSNorm).  The kernel above runs one 128-query tile per CTA with TWO passes over the keys; a pair block at 1 Mbp is 2048
+// such tiles of 8 short steps each, i.e. 13.8 waves of CTAs whose launch, set-up, Q / K latencies and epilogue are all
+// exposed: 0.29 ms per block alone (0.47 ms in the power-capped step) against a ~0.08 ms HBM floor.  What the r3
+// timing experiments and the SM-clock timeline (-DAGB_TRACE build) showed, in the order it was fixed:
+//   1. the epilogue's global traffic was half of the launch: TMEM hands a thread ONE ROW and rows are 512 B apart, so a
+//      warp instruction touched 32 lines x 16 B.  Now the four warps that share 32 rows exchange the finished tile
+//      through a swizzled staging buffer and every global access is 4 rows x 128 contiguous bytes (264 -> 189 us);
+//   2. a persistent CTA per SM with every role running ahead across tile boundaries (Q double-buffered in TMEM: dv = 128
+//      leaves 64 spare columns) hides set-up and load latency, but alone it bought only 290 -> 264 us, because
+//   3. each step is paced by the TMEM READ port: 16 warps x tcgen05.ld.32x32b.x32 = 64 KB per 128-key block at
+//      64 B/clk/SM = 1024 clk, and the two-pass scheme read S twice (row max, then exp) on top of computing it twice.
+//      This version is SINGLE-PASS: an online softmax with a running row maximum, and O is rescaled lazily — only when
+//      the maximum grows by more than 2^8 (the stale maximum just scales P and the row sum by the same factor, which
+//      the final division removes; bf16 / fp32 carry 2^8 without loss).  With four key blocks of comparable logits the
+//      rescale (a TMEM read-modify-write of O behind the previous P.V) practically never runs.  S is computed and read
+//      once, K streams through a ring instead of staying resident (any number of keys), and the freed shared memory
+//      holds the whole 128 x 128 fp32 tile for the epilogue exchange (one barrier instead of eight).
+// Roles: warp 0 TMA (K ring 2, V^T ring 2), warp 1 MMA issuer, warps 2-17 softmax + epilogue (lane quarter qd = warp & 3,
+// key quarter cq).  Barrier phases are carried in running counters.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kRowVBytes = 128 * kAttBN * 2;   // dv = 128: 32 KB per V^T block
+constexpr int kRowKStages = 2;
 // Bring-up timeline (only in a -DAGB_TRACE build, python -m alphagenome_b200.csrc.build --trace): CTA 0's TMA thread, MMA
 // thread and one softmax thread stamp (tag, SM clock) pairs into a global buffer that AGB_ROWATTN_TRACE=<file> dumps.
 #ifdef AGB_TRACE
@@ -549,9 +550,11 @@ constexpr int kRowVBytes = 128 * kAttBN * 2;   // dv = 128: 32 KB per V^T block
 #else
 #define ROW_TRACE(role, tag) do {} while (0)
 #endif
-constexpr int kRowStgBytes = 4 * 32 * 128;    // epilogue staging: per 32-row group, 32 rows x 32 fp32 columns, swizzled
-constexpr int kRowSmem = kAttKStages * kAttKBytes + 2 * kRowVBytes + 2 * kAttXchBytes + kRowStgBytes + 256;   // 217,344 B
+constexpr int kRowStgBytes = kAttBM * 128 * 4;    // epilogue staging: the whole tile, 128 rows x 128 fp32 channels, swizzled
+constexpr int kRowParBytes = 3 * 128 * 4;         // out_bias | norm_w | norm_b
+constexpr int kRowSmem = kRowKStages * kAttKBytes + 2 * kRowVBytes + 3 * kAttXchBytes + kRowStgBytes + kRowParBytes + 256;   // 204,544 B
 constexpr uint32_t kTmemQ1 = 384;   // second Q buffer (tile parity 1); parity 0 uses kTmemQ
+constexpr float kRescaleLog2 = 8.0f;   // O is rescaled only when the running maximum grows by more than 2^8
 
 __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __grid_constant__ AttnKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -559,35 +562,29 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
   constexpr int dv = 128;
 
   uint8_t* sK = smem;
-  uint8_t* sV = sK + kAttKStages * kAttKBytes;
-  float* xmax = reinterpret_cast<float*>(sV + 2 * kRowVBytes);   // [4][128] each
-  float* xsum = xmax + 4 * kAttBM;
-  uint8_t* stg_all = reinterpret_cast<uint8_t*>(xsum + 4 * kAttBM);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + kRowStgBytes);
+  uint8_t* sV = sK + kRowKStages * kAttKBytes;
+  uint8_t* stg_all = sV + 2 * kRowVBytes;
+  float* xmax = reinterpret_cast<float*>(stg_all + kRowStgBytes);   // [2 (block parity)][4][128]
+  float* xsum = xmax + 2 * 4 * kAttBM;                              // [4][128]
+  float* spar = xsum + 4 * kAttBM;                                  // out_bias | norm_w | norm_b
+  uint64_t* bars = reinterpret_cast<uint64_t*>(spar + 3 * 128);
   uint64_t* q_full = bars;         // [2]  Q rows of tile parity 0 / 1 are in TMEM (16 softmax warps arrive)
-  uint64_t* k_full = bars + 2;     // [4]
-  uint64_t* k_empty = bars + 6;    // [4]
-  uint64_t* v_full = bars + 10;    // [2]
-  uint64_t* v_empty = bars + 12;   // [2]
-  uint64_t* s_full = bars + 14;    // [2]
-  uint64_t* s_empty = bars + 16;   // [2]
-  uint64_t* p_full = bars + 18;    // [2 S stages][2 key halves]
-  uint64_t* o_full = bars + 22;    // [1]
-  uint64_t* o_empty = bars + 23;   // [1]  the epilogue has O in registers (16 softmax warps arrive)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* s_empty = bars + 12;   // [2]
+  uint64_t* p_full = bars + 14;    // [2 S stages][2 key halves]
+  uint64_t* o_full = bars + 18;    // [1]  the tile's last P.V has completed
+  uint64_t* o_empty = bars + 19;   // [1]  the epilogue has O in registers (16 softmax warps arrive)
+  uint64_t* pv_done = bars + 20;   // [1]  one phase per P.V product (a rescale of O waits for the product before it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nblk = p.nblk;          // 1..4 key blocks, the same for every tile
-  const int np1 = (p.dbg & 2) ? 0 : nblk;   // pass-1 steps (dbg bit 1: timing without the row-max pass)
-  // unit id -> (row = b * heads + h, q tiles [qt0, qt1))
-  auto decode = [&](int u, int& bh, int& qt0, int& qt1) {
-    if (u < p.rows_full) { bh = u; qt0 = 0; qt1 = p.q_tiles; return; }
-    const int t = u - p.rows_full;
-    bh = p.rows_full + t / p.upr;
-    qt0 = (t % p.upr) * p.u_tail;
-    qt1 = qt0 + p.u_tail < p.q_tiles ? qt0 + p.u_tail : p.q_tiles;
-  };
+  const int total = p.q_tiles * a.heads * a.batch;
+  const int nblk = p.nblk;          // key blocks per tile, the same for every tile
 
   if (warp == 0 && lane == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -598,18 +595,17 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
     tma_prefetch_desc(&p.tmV);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], kAttSmxWarps);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], kAttSmxWarps);
     }
-    for (int i = 0; i < kAttKStages; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-    }
     for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], kAttSmxWarps / 2);
     mbar_init(o_full, 1);
     mbar_init(o_empty, kAttSmxWarps);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -628,32 +624,25 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
   if (warp == 0) {
     // ---------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      uint32_t gv = 0;   // V^T blocks loaded so far
-      int iu = 0;
+      uint32_t gk = 0;   // key blocks loaded so far (K and V^T advance together)
       int trc = 0; (void)trc;
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++iu) {
-        int bh, qt0, qt1;
-        decode(u, bh, qt0, qt1);
-        const int h = bh % a.heads;
-        const int b = bh / a.heads;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int h = (tile / p.q_tiles) % a.heads;
+        const int b = tile / (p.q_tiles * a.heads);
         const int hk = a.kv_heads == 1 ? 0 : h;
-        // K: once per unit, resident for both passes of every q tile of the unit
-        for (int j = 0; j < nblk; ++j) {
-          mbar_wait(&k_empty[j], (uint32_t)(iu & 1) ^ 1u, 0x210u + j, p.err);   // released by the previous unit's last pass-2 product
+        for (int j = 0; j < nblk; ++j, ++gk) {
+          const int st = gk & 1;
+          const uint32_t ph = ((gk >> 1) & 1u) ^ 1u;
+          mbar_wait(&k_empty[st], ph, 0x210u + st, p.err);
           ROW_TRACE(0, 0x10 + j);
-          mbar_arrive_expect_tx(&k_full[j], kAttKBytes);
-          tma_load_4d(sK + j * kAttKBytes, &p.tmK, &k_full[j], 0, j * kAttBN, hk, b);
-          tma_load_4d(sK + j * kAttKBytes + kAttKBytes / 2, &p.tmK, &k_full[j], 64, j * kAttBN, hk, b);
-        }
-        for (int qt = qt0; qt < qt1; ++qt) {
-          for (int f = 0; f < nblk; ++f, ++gv) {
-            const int vs = gv & 1;
-            mbar_wait(&v_empty[vs], ((gv >> 1) & 1u) ^ 1u, 0x220u + vs, p.err);
-            ROW_TRACE(0, 0x20 + f);
-            mbar_arrive_expect_tx(&v_full[vs], kRowVBytes);
-            tma_load_4d(sV + vs * kRowVBytes, &p.tmV, &v_full[vs], f * kAttBN, 0, hk, b);
-            tma_load_4d(sV + vs * kRowVBytes + kRowVBytes / 2, &p.tmV, &v_full[vs], f * kAttBN + 64, 0, hk, b);
-          }
+          mbar_arrive_expect_tx(&k_full[st], kAttKBytes);
+          tma_load_4d(sK + st * kAttKBytes, &p.tmK, &k_full[st], 0, j * kAttBN, hk, b);
+          tma_load_4d(sK + st * kAttKBytes + kAttKBytes / 2, &p.tmK, &k_full[st], 64, j * kAttBN, hk, b);
+          mbar_wait(&v_empty[st], ph, 0x220u + st, p.err);
+          ROW_TRACE(0, 0x20 + j);
+          mbar_arrive_expect_tx(&v_full[st], kRowVBytes);
+          tma_load_4d(sV + st * kRowVBytes, &p.tmV, &v_full[st], j * kAttBN, 0, hk, b);
+          tma_load_4d(sV + st * kRowVBytes + kRowVBytes / 2, &p.tmV, &v_full[st], j * kAttBN + 64, 0, hk, b);
         }
       }
     }
@@ -663,68 +652,58 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(kAttBM, kAttBN);
       const uint32_t idesc_o = make_idesc_bf16(kAttBM, (uint32_t)dv);
-      const int nsteps = np1 + nblk;
-      uint32_t g = 0;    // QK^T products issued so far (S stage = g & 1)
-      uint32_t gv = 0;   // P.V products issued so far
-      uint32_t pc[2] = {0u, 0u};   // P tiles consumed per S stage
-      int it = 0, iu = 0;
+      uint32_t g = 0;    // QK^T products issued so far: S stage and K stage = g & 1
+      uint32_t gv = 0;   // P.V products issued so far: V stage = gv & 1 (the S stage its P lives in is also gv & 1)
+      int it = 0;
       int trc = 0; (void)trc;
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++iu) {
-        int bh, qt0, qt1;
-        decode(u, bh, qt0, qt1);
-      for (int qt = qt0; qt < qt1; ++qt, ++it) {
-        const bool first = qt == qt0, last = qt == qt1 - 1;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
         const uint32_t tmem_Q = tmem_base + ((it & 1) ? kTmemQ1 : kTmemQ);
         ROW_TRACE(1, 0x01);
         mbar_wait(&q_full[it & 1], (uint32_t)(it >> 1) & 1u, 0x200u + (it & 1), p.err);
         tc_fence_after();
         ROW_TRACE(1, 0x02);
-        for (int s = 0; s <= nsteps; ++s) {
-          if (s < nsteps) {
+        for (int s = 0; s <= nblk; ++s) {
+          if (s < nblk) {
             const int st = g & 1;
-            const int j = s < np1 ? s : s - np1;   // key block = K stage
-            if (first && s < nblk) mbar_wait(&k_full[j], (uint32_t)(iu & 1), 0x230u + j, p.err);   // later products find the block resident
+            mbar_wait(&k_full[st], (g >> 1) & 1u, 0x230u + st, p.err);
             mbar_wait(&s_empty[st], ((g >> 1) & 1u) ^ 1u, 0x240u + st, p.err);
             tc_fence_after();
             ROW_TRACE(1, 0x10 + s);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-              const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + j * kAttKBytes + (kk >> 2) * (kAttKBytes / 2)));
+              const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + st * kAttKBytes + (kk >> 2) * (kAttKBytes / 2)));
               tc_mma_bf16_ts(tmem_S + (uint32_t)st * kAttBN, tmem_Q + (uint32_t)(8 * kk), dk + (uint64_t)(2 * (kk & 3)), idesc_s,
                              kk > 0 ? 1u : 0u);
             }
-            if (last && s >= np1) tc_commit(&k_empty[j]);   // the stage may take the next unit's key block
+            tc_commit(&k_empty[st]);
             tc_commit(&s_full[st]);
             ++g;
           }
-          if (s >= 1 && (s - 1) >= np1) {
-            const int f = s - 1 - np1;
+          if (s >= 1) {
+            const int f = s - 1;
             const int vs = gv & 1;
-            const int pst = (g - (s < nsteps ? 2u : 1u)) & 1;   // the S stage step s-1 used
             mbar_wait(&v_full[vs], (gv >> 1) & 1u, 0x250u + vs, p.err);
             if (f == 0) {   // O still holds the previous tile until its epilogue has it in registers
               mbar_wait(o_empty, (uint32_t)(it & 1) ^ 1u, 0x280u, p.err);
-              tc_fence_after();
             }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-              mbar_wait(&p_full[pst * 2 + hf], pc[pst] & 1u, 0x260u + pst * 2 + hf, p.err);
+              mbar_wait(&p_full[vs * 2 + hf], (gv >> 1) & 1u, 0x260u + vs * 2 + hf, p.err);
               tc_fence_after();
               const uint64_t dvv = make_sw128_kmajor_desc(smem_u32(sV + vs * kRowVBytes + hf * (kRowVBytes / 2)));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t pa = tmem_S + (uint32_t)pst * kAttBN + (uint32_t)(32 * (2 * hf + (k >> 1)) + 8 * (k & 1));
+                const uint32_t pa = tmem_S + (uint32_t)vs * kAttBN + (uint32_t)(32 * (2 * hf + (k >> 1)) + 8 * (k & 1));
                 tc_mma_bf16_ts(tmem_O, pa, dvv + (uint64_t)(2 * k), idesc_o, (f > 0 || hf > 0 || k > 0) ? 1u : 0u);
               }
             }
             ROW_TRACE(1, 0x20 + f);
-            ++pc[pst];
             tc_commit(&v_empty[vs]);
+            tc_commit(pv_done);
             ++gv;
           }
         }
         tc_commit(o_full);
-      }
       }
     }
     __syncwarp();
@@ -737,19 +716,30 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
     const float sc_plain = a.scale * LOG2E;
-    const int rr = lane >> 3, cg = lane & 7;   // epilogue layout: rows 8 cq + rr (+ 4) of the group, channels 4 cg .. 4 cg + 3 of a chunk
-    uint8_t* stg = stg_all + qd * (32 * 128);
+    const int rr = lane >> 3, cg = lane & 7;   // epilogue layout: rows 8 cq + rr (+ 4) of the group, channels 4 cg .. 4 cg + 3 of a 32-wide chunk
+    uint8_t* stg = stg_all + qd * (32 * 512);   // this group's 32 rows x 512 B
     // the four warps of a 32-row group (same qd) only ever exchange data with each other: one named barrier per group
     auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + qd) : "memory"); };
 
+    {   // per-channel epilogue parameters: once per kernel into shared memory
+      const int t = threadIdx.x - 64;
+      if (t < 128) {
+        spar[t] = a.out_bias ? __ldg(a.out_bias + t) : 0.0f;
+        spar[128 + t] = __ldg(a.norm_w + t);
+        spar[256 + t] = __ldg(a.norm_b + t);
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+
     // Q rows of a tile: this thread's row, channels [32 cq, 32 cq + 32) = 16 packed TMEM columns
-    auto q_load = [&](int bh, int qt, uint32_t (&qr)[16]) {
-      const int h = bh % a.heads;
-      const int b = bh / a.heads;
+    auto q_load = [&](int tile, uint32_t (&qr)[16]) {
+      const int qt = tile % p.q_tiles;
+      const int h = (tile / p.q_tiles) % a.heads;
+      const int b = tile / (p.q_tiles * a.heads);
       const int row = qt * kAttBM + lrow;
 #pragma unroll
       for (int j = 0; j < 16; ++j) qr[j] = 0u;
-      if (row < a.n_q && !(p.dbg & 8)) {
+      if (row < a.n_q) {
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.Q) + (long)b * a.q_bstride +
                                                           (long)h * a.q_hstride + (long)row * a.q_ld + 32 * cq);
 #pragma unroll
@@ -766,84 +756,79 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_full[parity]);
     };
-    if ((int)blockIdx.x < p.total_units) {
-      int bh, qt0, qt1;
-      decode(blockIdx.x, bh, qt0, qt1);
+    if ((int)blockIdx.x < total) {
       uint32_t qr[16];
-      q_load(bh, qt0, qr);
+      q_load(blockIdx.x, qr);
       q_publish(0, qr);
     }
 
-    uint32_t g = 0;
+    uint32_t g = 0;    // key blocks processed so far (all tiles): S stage = g & 1, the P.V product of block g is product g
     int it = 0;
     int trc = (warp == 2 && lane == 0) ? 0 : 4096; (void)trc;
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-      int bh, qt0, qt1;
-      decode(u, bh, qt0, qt1);
-      const int h = bh % a.heads;
-      const int b = bh / a.heads;
-    for (int qt = qt0; qt < qt1; ++qt, ++it) {
-      // the tile after this one: the next q tile of the unit, or the first of this CTA's next unit
-      int nbh = bh, nqt = qt + 1;
-      bool has_next = nqt < qt1;
-      if (!has_next && u + (int)gridDim.x < p.total_units) {
-        int e;
-        decode(u + gridDim.x, nbh, nqt, e);
-        has_next = true;
-      }
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int qt = tile % p.q_tiles;
+      const int h = (tile / p.q_tiles) % a.heads;
+      const int b = tile / (p.q_tiles * a.heads);
+      const int next = tile + gridDim.x;
       ROW_TRACE(2, 0x01);
       uint32_t qn[16];
-      if (has_next) q_load(nbh, nqt, qn);   // in flight during pass 1
+      if (next < total) q_load(next, qn);   // in flight during the first key block
 
-      // ---- pass 1: exact row maximum ----
-      float rowmax = -INFINITY;
-      for (int s = 0; s < np1; ++s, ++g) {
-        const int st = g & 1;
-        const int key0 = s * kAttBN + cq * 32;
-        mbar_wait(&s_full[st], (g >> 1) & 1u, 0x270u + st, p.err);
-        tc_fence_after();
-        ROW_TRACE(2, 0x10 + s);
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_off + (uint32_t)st * kAttBN + (uint32_t)cq * 32, r);
-        tmem_ld_wait();
-        if (key0 + 32 <= a.n_k) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rowmax = fmaxf(rowmax, __uint_as_float(r[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (key0 + j < a.n_k) rowmax = fmaxf(rowmax, __uint_as_float(r[j]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[st]);
-      }
-      ROW_TRACE(2, 0x02);
-      xmax[cq * kAttBM + lrow] = rowmax;
-      group_sync();
-      ROW_TRACE(2, 0x03);
-      rowmax = fmaxf(fmaxf(xmax[lrow], xmax[kAttBM + lrow]), fmaxf(xmax[2 * kAttBM + lrow], xmax[3 * kAttBM + lrow]));
-      const float mneg = np1 ? -rowmax * sc_plain : 0.0f;
-      // the other Q buffer was last read by the tile before this one, whose products all completed long ago
-      if (has_next) q_publish((it + 1) & 1, qn);
-      ROW_TRACE(2, 0x04);
-
-      // ---- pass 2: p = exp(logit - max) -> P (bf16, over the S columns just read) ----
-      float rsum[4] = {0.f, 0.f, 0.f, 0.f};
+      float m_run = 0.0f;                      // running row maximum (raw logits), set by the first block
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f};    // partial row sums of the weights, in units of exp(- m_run * scale)
       for (int s = 0; s < nblk; ++s, ++g) {
         const int st = g & 1;
         const int key0 = s * kAttBN + cq * 32;
         mbar_wait(&s_full[st], (g >> 1) & 1u, 0x270u + st, p.err);
         tc_fence_after();
-        ROW_TRACE(2, 0x20 + s);
+        ROW_TRACE(2, 0x10 + s);
         const uint32_t s_addr = tmem_S + lane_off + (uint32_t)st * kAttBN + (uint32_t)cq * 32;
         uint32_t r[32];
         tmem_ld_32x32(s_addr, r);
         tmem_ld_wait();
+        const bool full = key0 + 32 <= a.n_k;
+        float bmax = -INFINITY;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bmax = fmaxf(bmax, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (key0 + j < a.n_k) bmax = fmaxf(bmax, __uint_as_float(r[j]));
+        }
+        // block maximum of the row: the four key quarters exchange theirs (buffers alternate, one barrier per block)
+        float* xm = xmax + (s & 1) * 4 * kAttBM;
+        xm[cq * kAttBM + lrow] = bmax;
+        group_sync();
+        bmax = fmaxf(fmaxf(xm[lrow], xm[kAttBM + lrow]), fmaxf(xm[2 * kAttBM + lrow], xm[3 * kAttBM + lrow]));
+        if (s == 0) {
+          m_run = bmax;
+          if (next < total) q_publish((it + 1) & 1, qn);   // that Q buffer was last read by the tile before this one
+        } else {
+          // lazy rescale: all four warps of the group see the same (m_run, bmax), so they take the same branch per row
+          const bool grow = (bmax - m_run) * sc_plain > kRescaleLog2;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float fac = grow ? ex2_approx((m_run - bmax) * sc_plain) : 1.0f;
+            if (grow) m_run = bmax;
+            rsum[0] *= fac; rsum[1] *= fac; rsum[2] *= fac; rsum[3] *= fac;
+            // O holds the products of blocks 0 .. s-1: product g-1 must have completed before it is scaled in place
+            mbar_wait(pv_done, (g - 1) & 1u, 0x2A0u, p.err);
+            tc_fence_after();
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(cq * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * fac);
+            tmem_st_32x16(tmem_O + lane_off + (uint32_t)(cq * 32), reinterpret_cast<uint32_t(&)[16]>(o[0]));
+            tmem_st_32x16(tmem_O + lane_off + (uint32_t)(cq * 32 + 16), reinterpret_cast<uint32_t(&)[16]>(o[16]));
+            tmem_st_wait();   // ordered before the P.V of this block by the fence + p_full arrive below
+          }
+        }
+        const float mneg = -m_run * sc_plain;
         float pv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pv[j] = (p.dbg & 4) ? fmaf(__uint_as_float(r[j]), sc_plain, mneg) : ex2_approx(fmaf(__uint_as_float(r[j]), sc_plain, mneg));
-        if (key0 + 32 > a.n_k) {
+        for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), sc_plain, mneg));
+        if (!full) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (key0 + j >= a.n_k) pv[j] = 0.0f;
@@ -865,15 +850,12 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
       }
 
       // ---- epilogue: O / rowsum + to_v bias + residual (fp32), RMSNormWithBias of the finished row (bf16) ----
-      // TMEM hands a thread ONE ROW (rows are 512 B apart in global memory), so loading the residual and storing out /
-      // norm_out straight from that layout touches 32 different 128-byte lines per warp instruction, 16 bytes each:
-      // with it the launch takes 264 us, without any epilogue traffic 138 us (timing experiment, P = 512).  The four
-      // warps that share 32 rows therefore exchange the tile through a swizzled 4 KB staging buffer, 32 columns at a
-      // time: warp cq then owns rows 8 cq .. 8 cq + 7 of the group with lanes across the channels, so every global
-      // access is 4 rows x 128 contiguous bytes.
+      // TMEM hands a thread ONE ROW and rows are 512 B apart in global memory, so the four warps that share 32 rows exchange
+      // the tile through the swizzled staging buffer: warp cq then owns rows 8 cq .. 8 cq + 7 of the group with lanes across
+      // the channels, and every global access is 4 rows x 128 contiguous bytes.
       const int r0 = qt * kAttBM + qd * 32 + cq * 8 + rr;       // this lane's rows: r0 and r0 + 4
       const long ob = (long)b * a.out_bstride + (long)h * a.out_hstride;
-      const bool ok0 = r0 < a.n_q && !(p.dbg & 1), ok1 = r0 + 4 < a.n_q && !(p.dbg & 1);
+      const bool ok0 = r0 < a.n_q, ok1 = r0 + 4 < a.n_q;
       // y starts as the residual (requested now, in flight while the last P.V drains) and ends as the finished row
       float y[32];      // [chunk][row 0: 4 channels | row 1: 4 channels]
 #pragma unroll
@@ -894,36 +876,33 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
       mbar_wait(o_full, (uint32_t)(it & 1), 0x290u, p.err);
       tc_fence_after();
       ROW_TRACE(2, 0x06);
+      {
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(cq * 32), o);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);   // O is in registers: the next tile's P.V may overwrite it
+        // element (row, 16-byte unit u) of the group's tile lives at unit u ^ (row & 7): conflict-free both ways
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<float4*>(stg + lane * 512 + (((cq * 8 + u) ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(o[4 * u]) * inv, __uint_as_float(o[4 * u + 1]) * inv, __uint_as_float(o[4 * u + 2]) * inv,
+                          __uint_as_float(o[4 * u + 3]) * inv);
+      }
+      group_sync();
       float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[8];
-        tmem_ld_32x8(tmem_O + lane_off + (uint32_t)(c * 32 + cq * 8), r);
-        tmem_ld_wait();
-        if (c == 3) {                             // O is in registers: the next tile's P.V may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(o_empty);
-        }
-        if (c > 0) group_sync();                  // the previous chunk has been read by all four warps
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          *reinterpret_cast<float4*>(stg + lane * 128 + (((cq * 2 + u) ^ (lane & 7)) << 4)) =
-              make_float4(__uint_as_float(r[4 * u]) * inv, __uint_as_float(r[4 * u + 1]) * inv, __uint_as_float(r[4 * u + 2]) * inv,
-                          __uint_as_float(r[4 * u + 3]) * inv);
-        group_sync();
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.out_bias) bb = __ldg(reinterpret_cast<const float4*>(a.out_bias + c * 32 + cg * 4));
+        const float4 bb = *reinterpret_cast<const float4*>(spar + c * 32 + cg * 4);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int gr = cq * 8 + rr + 4 * i;     // row inside the group
-          float4 v = *reinterpret_cast<const float4*>(stg + gr * 128 + ((cg ^ (gr & 7)) << 4));
-          v.x = (v.x + bb.x) + y[8 * c + 4 * i]; v.y = (v.y + bb.y) + y[8 * c + 4 * i + 1];     // same order as the
-          v.z = (v.z + bb.z) + y[8 * c + 4 * i + 2]; v.w = (v.w + bb.w) + y[8 * c + 4 * i + 3]; // one-tile kernel: bit-identical
-          const bool ok = i ? ok1 : ok0;
-          if (ok) {
+          float4 v = *reinterpret_cast<const float4*>(stg + gr * 512 + (((c * 8 + cg) ^ (gr & 7)) << 4));
+          v.x = (v.x + bb.x) + y[8 * c + 4 * i]; v.y = (v.y + bb.y) + y[8 * c + 4 * i + 1];
+          v.z = (v.z + bb.z) + y[8 * c + 4 * i + 2]; v.w = (v.w + bb.w) + y[8 * c + 4 * i + 3];
+          if (i ? ok1 : ok0)
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + ob + (long)(r0 + 4 * i) * a.out_ld + c * 32 + cg * 4) = v;
-          }
           const float sq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
           if (i) ss1 += sq; else ss0 += sq;
           y[8 * c + 4 * i] = v.x; y[8 * c + 4 * i + 1] = v.y; y[8 * c + 4 * i + 2] = v.z; y[8 * c + 4 * i + 3] = v.w;
@@ -939,8 +918,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
       const float rinv0 = rsqrtf(ss0 * (1.0f / 128.0f) + 1e-5f), rinv1 = rsqrtf(ss1 * (1.0f / 128.0f) + 1e-5f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(a.norm_w + c * 32 + cg * 4));
-        const float4 nb4 = __ldg(reinterpret_cast<const float4*>(a.norm_b + c * 32 + cg * 4));
+        const float4 w = *reinterpret_cast<const float4*>(spar + 128 + c * 32 + cg * 4);
+        const float4 nb4 = *reinterpret_cast<const float4*>(spar + 256 + c * 32 + cg * 4);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           if (!(i ? ok1 : ok0)) continue;
@@ -952,7 +931,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) row_attention_kernel(const __g
           *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.norm_out) + ob + (long)(r0 + 4 * i) * a.out_ld + c * 32 + cg * 4) = pk;
         }
       }
-    }
+      ROW_TRACE(2, 0x08);
     }
     tc_fence_before();
   }
@@ -1024,13 +1003,9 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
     uint32_t box[4] = {64, (uint32_t)a.dv, 1, 1};
     if (int rc = make_tensor_map_bf16(&p.tmV, a.Vt, 4, dims, str, box)) return rc;
   }
-  if (a.mode == 1 && a.norm_out != nullptr && a.dv == 128 && p.nblk <= kAttKStages && rowattn_persistent()) {
+  if (a.mode == 1 && a.norm_out != nullptr && a.dv == 128 && rowattn_persistent()) {
     const long tiles = (long)p.q_tiles * a.heads * a.batch;
     if (tiles > 1073741823L) return set_error("ag_attention_fwd: grid too large");
-    {
-      const char* e = getenv("AGB_ROWATTN_DBG");
-      p.dbg = e ? atoi(e) : 0;
-    }
     static thread_local unsigned char attr_done[64];
     if (!attr_done[device]) {
       cudaError_t e = cudaFuncSetAttribute(row_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem);
@@ -1038,32 +1013,9 @@ int launch_attention(const AgAttnArgs& a, int device, cudaStream_t stream) {
       attr_done[device] = 1;
     }
     const int sms = sm_count(device);
-    // Work units.  A CTA that keeps a row's K resident across all its q tiles reads K once instead of q_tiles times (the
-    // kernel is L2->SM bound: K + V^T of a row are 256 KB, 1 MB per row when every q tile fetches both), but whole rows
-    // quantise badly (512 rows on 148 SMs = 3.46 rows each), so only the first floor(rows / G) * G rows are whole-row
-    // units and the rest are cut into units of u_tail q tiles, u_tail chosen for the shortest schedule (ties: larger).
-    const int rows = a.heads * a.batch;
-    const int G = tiles < sms ? (int)tiles : sms;
-    p.rows_full = (rows / G) * G;
-    const int tail = rows - p.rows_full;
-    p.u_tail = p.q_tiles;
-    if (tail > 0) {
-      long best = -1;
-      for (int u = p.q_tiles; u >= 1; --u) {
-        const long units = (long)tail * ((p.q_tiles + u - 1) / u);
-        const long cost = ((units + G - 1) / G) * u;
-        if (best < 0 || cost < best) { best = cost; p.u_tail = u; }
-      }
-    }
-    {
-      const char* e = getenv("AGB_ROWATTN_UNITS");   // 0: every q tile its own unit (K reloaded per tile)
-      if (e && e[0] == '0') { p.rows_full = 0; p.u_tail = 1; }
-    }
-    p.upr = (p.q_tiles + p.u_tail - 1) / p.u_tail;
-    p.total_units = p.rows_full + (rows - p.rows_full) * p.upr;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(p.total_units < G ? p.total_units : G), 1, 1);   // persistent: one CTA per SM
+    cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms), 1, 1);   // persistent: one CTA per SM; the q tiles of a row run side by side (L2)
     cfg.blockDim = dim3(kAttThreads, 1, 1);
     cfg.dynamicSmemBytes = kRowSmem;
     cfg.stream = stream;

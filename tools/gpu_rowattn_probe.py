@@ -1,6 +1,5 @@
 """Row attention (ag_attention_fwd mode 1 with the fused RMSNorm, as the pair block calls it) alone at P x P cells:
-CUDA-event time per launch.  AGB_ROWATTN=0 selects the one-tile-per-CTA kernel; AGB_ROWATTN_DBG masks are timing
-experiments of the persistent kernel (results invalid).
+CUDA-event time per launch.  AGB_ROWATTN=0 selects the one-tile-per-CTA two-pass kernel.
 
     python tools/gpu_rowattn_probe.py [P] [launches]
 """
