@@ -17,6 +17,7 @@ Weights are packed once per parameter version (bf16, [taps][C_out][C_in]; norms 
 from __future__ import annotations
 
 import math
+import os
 import weakref
 from typing import Dict, Optional
 
@@ -359,7 +360,7 @@ class TrunkEngine:
         # product rides along as a second operand pair of the width-5 GEMM (+1.7 % MMA work), both biases summed —
         # so at 1 Mbp the 3.2 GB fp32 x0 is neither written nor read back.  A pointwise norm that re-estimates its
         # variance needs x0's statistics, hence x0 itself: that (default-constructed, updating) case keeps the plain form.
-        fuse_x0 = self._updating(pw["s"]) is None
+        fuse_x0 = self._updating(pw["s"]) is None and os.environ.get("AGB_EMBED_FUSE", "1") != "0"   # (=0: A/B timing)
         x0 = None if fuse_x0 else torch.empty(B, L, C0, **f32)
         self._gemm(X, e["W"], pre_shift=e["b"], out=x0, actA=Act(a0, pw["s"], pw["t"], ACT_GELU1702))
         ups = P["ups"]

@@ -62,29 +62,46 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []      # (host arrival time, line)
         self.proc = None
+        self.t0 = self.t1 = None
 
-    def start(self):
+    def start(self, wait_s: float = 3.0):
+        """Launch nvidia-smi (its start-up alone can outlast a 0.3 s timed region) and wait for its first row; the rows
+        that count are those arriving between mark_begin() and mark_end()."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.time() + wait_s
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.mark_end()
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        lo = self.t0 if self.t0 is not None else 0.0
+        # a row describes the ~50 ms before it was printed: accept rows printed up to one period after the region ended
+        rows = [r for t, r in self.rows if lo <= t <= self.t1 + 0.06]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -365,15 +382,17 @@ def main():
     B, L = wl.B, wl.L
     units = B * L * (world if args.dp else 1)     # bp the whole job processes per step
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         wl.step()
     barrier(world)
 
     # --- timed: device-resident inputs ---
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ms = time_steps(wl.step, args.steps, world)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
 
     # --- timed: end to end through the public API with host buffers ---
