@@ -16,7 +16,10 @@
 //                      fused affine / ReLU / residual / scale / activation / maxpool2 -> 128-bit global accesses.
 //                      The kernel is instantiated per set of enabled outputs (template FLAGS) so disabled paths
 //                      cost no instructions; all pointer arithmetic is hoisted to one 64-bit base per tile.
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -55,10 +58,19 @@ struct GemmKParams {
   int n_tile, m_tiles, n_tiles, total_tiles, kblocks;   // m_tiles counts (128 * CG)-row tiles
   int n_last;                                           // width of N tile n_tiles-1 (mixed-width tiling: k x n_tile + remainder)
   int kblocks2;                                         // 64-deep K blocks of the second operand pair (0 = none)
-  int stream_res;                                       // residual rows bypass L1 (env AGB_EPI_STREAM=1; A/B timing only — measured slower)
   int a_bmask;                                          // 0 when A is shared by every batch (a_bstride == 0), else -1
   unsigned int* err;
+  unsigned long long* trace;   // -DAGB_TRACE builds only (AGB_GEMM_TRACE=<file>): CTA 0's per-role SM-clock timeline
 };
+
+#ifdef AGB_TRACE
+#define GEMM_TRACE(role, tag)                                                                                     \
+  do {                                                                                                            \
+    if (p.trace && blockIdx.x == 0 && trc < 2040) p.trace[(role) * 2048 + trc++] = ((unsigned long long)(tag) << 48) | (unsigned long long)(clock64() & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#else
+#define GEMM_TRACE(role, tag) do {} while (0)
+#endif
 
 // GEMM epilogue activations (checked on the host): ACT_NONE / ACT_GELU1702 for bf16 and fp32 outputs; fp32 outputs
 // also take the prediction heads' ACT_SOFTPLUS_MUL (softplus(v + shift) * scale, AG:1388-1393) and ACT_SIGMOID (AG:1321).
@@ -66,7 +78,15 @@ __device__ __forceinline__ float gelu1702_fast(float x) {   // 0.5x + 0.5x*tanh(
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx(0.851f * x), hx);
 }
-__device__ __forceinline__ float gelu1702_acc(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+// x * sigmoid(1.702 x) for fp32 outputs: x * rcp(1 + 2^(-1.702 log2(e) x)), two MUFU ops and three FMA-pipe ops (the
+// __expf / __fdividef intrinsics wrap the same two MUFU ops in range fix-ups — 5 more instructions per element — that
+// cannot trigger here: 2^t overflowing to +inf gives rcp(inf) = 0, the correct limit)
+__device__ __forceinline__ float gelu1702_acc(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.4554669595930157f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 // F.softplus (beta 1, threshold 20): max(x, 0) + log1p(exp(-|x|)); the log1p argument is at most 1
 __device__ __forceinline__ float softplus_acc(float x) {
   const float t = __expf(-fabsf(x));
@@ -74,6 +94,15 @@ __device__ __forceinline__ float softplus_acc(float x) {
   return fmaxf(x, 0.0f) + l;
 }
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void store_bf16x4(char* dst, const float4& y) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(y.z, y.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = pk;
+}
 
 // One activated output for 4 consecutive channels of one row: dst = act(v*s + t), bf16 (fast GELU) or fp32.
 __device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool is_bf16, int act, float4 v,
@@ -123,6 +152,48 @@ __device__ __forceinline__ void epi_store4(char* base, uint32_t elem_off, bool i
   }
 }
 
+// The same for the NG (row, 4-channel) groups a lane owns in one chunk, with the run-time format decided ONCE for all of
+// them, so that the NG x 4 independent FMA -> MUFU -> store chains overlap.
+template <int NG>
+__device__ __forceinline__ void epi_store_groups(char* base, const uint32_t (&row)[NG], const bool (&ok)[NG], uint32_t ld, uint32_t col,
+                                                 bool is_bf16, int act, const float4 (&v)[NG], const float4& s, const float4& t) {
+  if (is_bf16) {
+    if (act != ACT_NONE) {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        const float4 y = make_float4(gelu1702_fast(fmaf(v[k].x, s.x, t.x)), gelu1702_fast(fmaf(v[k].y, s.y, t.y)),
+                                     gelu1702_fast(fmaf(v[k].z, s.z, t.z)), gelu1702_fast(fmaf(v[k].w, s.w, t.w)));
+        if (ok[k]) store_bf16x4(base + (size_t)(row[k] * ld + col) * 2, y);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        const float4 y = make_float4(fmaf(v[k].x, s.x, t.x), fmaf(v[k].y, s.y, t.y), fmaf(v[k].z, s.z, t.z), fmaf(v[k].w, s.w, t.w));
+        if (ok[k]) store_bf16x4(base + (size_t)(row[k] * ld + col) * 2, y);
+      }
+    }
+  } else if (act == ACT_GELU1702) {
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      const float4 y = make_float4(gelu1702_acc(fmaf(v[k].x, s.x, t.x)), gelu1702_acc(fmaf(v[k].y, s.y, t.y)),
+                                   gelu1702_acc(fmaf(v[k].z, s.z, t.z)), gelu1702_acc(fmaf(v[k].w, s.w, t.w)));
+      if (ok[k]) *reinterpret_cast<float4*>(base + (size_t)(row[k] * ld + col) * 4) = y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NG; ++k)
+      if (ok[k]) epi_store4(base, row[k] * ld + col, false, act, v[k], s, t);
+  }
+}
+__device__ __forceinline__ void epi_store4x4(char* base, const uint32_t (&row)[4], const bool (&ok)[4], uint32_t ld, uint32_t col, bool is_bf16,
+                                             int act, const float4 (&v)[4], const float4& s, const float4& t) {
+  epi_store_groups<4>(base, row, ok, ld, col, is_bf16, act, v, s, t);
+}
+__device__ __forceinline__ void epi_store2x4(char* base, const uint32_t (&row)[2], const bool (&ok)[2], uint32_t ld, uint32_t col, bool is_bf16,
+                                             int act, const float4 (&v)[2], const float4& s, const float4& t) {
+  epi_store_groups<2>(base, row, ok, ld, col, is_bf16, act, v, s, t);
+}
+
 // Per-channel epilogue parameters are re-read by every tile: keep them in what little L1 the 226 KB of shared memory
 // leaves (evict_last).  ncu (profiles/ncu_r02_summary.md): 39 % of the HBM-bound w1 GEMM's stall samples sit on the first
 // FFMA after the staging read (long scoreboard).  Letting the residual rows bypass L1 (no_allocate, ldg4_stream) was
@@ -143,11 +214,6 @@ __device__ __forceinline__ float4 shfl4(const float4& v, int src) {
   r.z = __shfl_sync(0xffffffffu, v.z, src);
   r.w = __shfl_sync(0xffffffffu, v.w, src);
   return r;
-}
-__device__ __forceinline__ float4 ldg4_stream(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
 }
 
 template <int FLAGS, int CG>
@@ -218,7 +284,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int trc = 0; (void)trc;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        GEMM_TRACE(0, 0x01);
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
         const int mt = rest % p.m_tiles;
@@ -273,9 +341,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      int trc = 0; (void)trc;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        GEMM_TRACE(1, 0x01);
         mbar_wait(&tempty_bar[as], aphase ^ 1u, 0x30u + as, p.err);
         tc_fence_after();
+        GEMM_TRACE(1, 0x02);
         const uint32_t idesc = (tile % p.n_tiles == p.n_tiles - 1) ? idesc_last : idesc_full;
         const uint32_t d_tmem = tmem_base + (uint32_t)as * kMaxNTile;
         for (int it = 0; it < iters; ++it) {
@@ -294,6 +365,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           if constexpr (CG == 2) tc_commit_cg2(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        GEMM_TRACE(1, 0x03);
         if constexpr (CG == 2) tc_commit_cg2(&tfull_bar[as]); else tc_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
@@ -317,6 +389,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
     const uint32_t st_x = st_line & 7;
     int as = 0;
     uint32_t aphase = 0;
+    int trc = (warp == 2 && lane == 0) ? 0 : 4096; (void)trc;
     const float post = g.post_scale ? __ldg(g.post_scale) : 1.0f;
     const bool relu = g.relu != 0;
     const bool a16 = g.actA.dtype == 0, b16 = g.actB.dtype == 0, p16 = g.actP.dtype == 0;
@@ -365,10 +438,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
       const int res_cols = kRes ? g.res_ch - n0 : 0;   // residual applies to in-tile columns < res_cols
       const int rows_left = g.M - row_t;               // in-tile rows >= rows_left do not exist
 
+      GEMM_TRACE(2, 0x01);
       mbar_wait(&tfull_bar[as], aphase, 0x40u + as, p.err);
       tc_fence_after();
+      GEMM_TRACE(2, 0x02);
       const uint32_t t_addr = tmem_base + ((uint32_t)lr_base << 16) + (uint32_t)as * kMaxNTile;
 
+      // kG = false: every row of the tile exists (all tiles but the last M tile): no per-row predicates, so the
+      // compiler keeps one straight-line body and overlaps the 16 elements' chains instead of branching per row group
+      auto run_chunks = [&](auto guard) {
+      constexpr bool kG = decltype(guard)::value;
       for (int ch = slot; ch < nchunks; ch += 4) {
         const int col = ch * kEpiCols + 4 * cg;  // in-tile column of this lane's 4 channels
         // ---- residual rows first: in flight while the accumulators travel TMEM -> registers -> smem ----
@@ -379,14 +458,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
           for (int k = 0; k < 4; ++k) {
             const int lr = lr_base + 2 * rsel + ((k & 1) ^ (rsel & 1)) + 16 * (k >> 1);
             rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (on && lr < rows_left)
-              rr[k] = p.stream_res ? ldg4_stream(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col))
-                                   : __ldg(reinterpret_cast<const float4*>(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col)));
+            if (on && (!kG || lr < rows_left))
+              rr[k] = __ldg(reinterpret_cast<const float4*>(res_t + (uint32_t)((lr >> g.res_shift) * g.res_ld + col)));
           }
         }
+        GEMM_TRACE(2, 0x10);
         uint32_t r[16];
         tmem_ld_32x16(t_addr + (uint32_t)(ch * kEpiCols), r);
         tmem_ld_wait();
+        GEMM_TRACE(2, 0x11);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(st_wr + (((st_u0 + j) ^ st_x) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -398,53 +478,77 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_conv_kernel(const __grid
         if constexpr (kActB) { sB = shfl4(regB, psrc); tB = shfl4(regB, psrc + 16); }
         if (has_actP) { sP = shfl4(regP, psrc); tP = shfl4(regP, psrc + 16); }
         __syncwarp();
+        GEMM_TRACE(2, 0x12);
 
+        // The four (row, 4-channel) groups of this lane are processed TOGETHER, stage by stage: the output formats are
+        // run-time values, and as one call per group (the first version) every group's FMA -> MUFU -> store chain sat
+        // behind its own reconvergence point, i.e. the warp had 4 independent elements in flight instead of 16.  The
+        // SM-clock timeline (-DAGB_TRACE) showed the consequence on the epilogue-bound launches (w1 convs, output
+        // embedding, K <= 128 linears): the MMA thread waited for a free accumulator 30-50 % of every tile.
+        float4 x[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          float4 v[2];
-#pragma unroll
-          for (int stp = 0; stp < 2; ++stp) {
-            // odd row-selectors take their odd row first: the two rows a quarter-warp reads in one LDS.128 then
-            // differ in parity and hit disjoint bank groups of the swizzled staging tile
-            const int wr = 2 * rsel + (stp ^ (rsel & 1)) + 16 * i;   // row inside this warp's 32
-            const int lr = lr_base + wr;                              // row inside the tile
-            const uint32_t line = (uint32_t)(wr >> 1);
-            float4 x = *reinterpret_cast<const float4*>(stg + line * 128 + ((((uint32_t)(wr & 1) * 4 + cg) ^ (line & 7)) << 4));
-            x.x = fmaf(x.x, ps.x, pt.x);
-            x.y = fmaf(x.y, ps.y, pt.y);
-            x.z = fmaf(x.z, ps.z, pt.z);
-            x.w = fmaf(x.w, ps.w, pt.w);
-            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            if constexpr (kRes) {
-              const float4 ra = rr[i * 2 + stp];
-              x.x += ra.x; x.y += ra.y; x.z += ra.z; x.w += ra.w;
-            }
-            x.x *= post; x.y *= post; x.z *= post; x.w *= post;
-            if (lr < rows_left) {
-              if constexpr (kOut) *reinterpret_cast<float4*>(out_t + (size_t)(uint32_t)(lr * g.out_ld + col) * 4) = x;
-              if constexpr (kActA) epi_store4(actA_t, (uint32_t)(lr * g.actA.ld + col), a16, aG, x, sA, tA);
-              if constexpr (kActB) epi_store4(actB_t, (uint32_t)(lr * g.actB.ld + col), b16, bG, x, sB, tB);
-            }
-            v[stp] = x;
+        for (int k = 0; k < 4; ++k) {
+          // k = 2 i + stp: odd row-selectors take their odd row first, so the two rows a quarter-warp reads in one
+          // LDS.128 differ in parity and hit disjoint bank groups of the swizzled staging tile
+          const int wr = 2 * rsel + ((k & 1) ^ (rsel & 1)) + 16 * (k >> 1);   // row inside this warp's 32
+          const uint32_t line = (uint32_t)(wr >> 1);
+          float4 v = *reinterpret_cast<const float4*>(stg + line * 128 + ((((uint32_t)(wr & 1) * 4 + cg) ^ (line & 7)) << 4));
+          v.x = fmaf(v.x, ps.x, pt.x);
+          v.y = fmaf(v.y, ps.y, pt.y);
+          v.z = fmaf(v.z, ps.z, pt.z);
+          v.w = fmaf(v.w, ps.w, pt.w);
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if constexpr (kRes) {
+            const float4 ra = rr[k];
+            v.x += ra.x; v.y += ra.y; v.z += ra.z; v.w += ra.w;
           }
-          if constexpr (kPool) {
+          v.x *= post; v.y *= post; v.z *= post; v.w *= post;
+          x[k] = v;
+        }
+        bool rowok[4];
+        uint32_t lrk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          lrk[k] = (uint32_t)(lr_base + 2 * rsel + ((k & 1) ^ (rsel & 1)) + 16 * (k >> 1));   // row inside the tile
+          rowok[k] = !kG || (int)lrk[k] < rows_left;
+        }
+        if constexpr (kOut) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (rowok[k]) *reinterpret_cast<float4*>(out_t + (size_t)(lrk[k] * (uint32_t)g.out_ld + (uint32_t)col) * 4) = x[k];
+        }
+        if constexpr (kActA) epi_store4x4(actA_t, lrk, rowok, (uint32_t)g.actA.ld, (uint32_t)col, a16, aG, x, sA, tA);
+        if constexpr (kActB) epi_store4x4(actB_t, lrk, rowok, (uint32_t)g.actB.ld, (uint32_t)col, b16, bG, x, sB, tB);
+        if constexpr (kPool) {
+          float4 pv[2];
+          bool pok[2];
+          uint32_t prk[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            pv[i].x = fmaxf(x[2 * i].x, x[2 * i + 1].x);
+            pv[i].y = fmaxf(x[2 * i].y, x[2 * i + 1].y);
+            pv[i].z = fmaxf(x[2 * i].z, x[2 * i + 1].z);
+            pv[i].w = fmaxf(x[2 * i].w, x[2 * i + 1].w);
             const int lr = lr_base + 2 * rsel + 16 * i;   // even row of the pair
-            if (lr + 1 < rows_left) {
-              float4 pv;
-              pv.x = fmaxf(v[0].x, v[1].x);
-              pv.y = fmaxf(v[0].y, v[1].y);
-              pv.z = fmaxf(v[0].z, v[1].z);
-              pv.w = fmaxf(v[0].w, v[1].w);
-              const int pr = lr >> 1;
-              if (has_poolf) *reinterpret_cast<float4*>(pool_t + (size_t)(uint32_t)(pr * g.pool_ld + col) * 4) = pv;
-              if (has_actP) epi_store4(actP_t, (uint32_t)(pr * g.actP.ld + col), p16, pG, pv, sP, tP);
-            }
+            pok[i] = !kG || lr + 1 < rows_left;
+            prk[i] = (uint32_t)(lr >> 1);
           }
+          if (has_poolf) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              if (pok[i]) *reinterpret_cast<float4*>(pool_t + (size_t)(prk[i] * (uint32_t)g.pool_ld + (uint32_t)col) * 4) = pv[i];
+          }
+          if (has_actP) epi_store2x4(actP_t, prk, pok, (uint32_t)g.actP.ld, (uint32_t)col, p16, pG, pv, sP, tP);
         }
         __syncwarp();
+        GEMM_TRACE(2, 0x13);
       }
+      };
+      if (rows_left >= kBlockM) run_chunks(std::false_type{});
+      else run_chunks(std::true_type{});
       tc_fence_before();
       __syncwarp();
+      GEMM_TRACE(2, 0x03);
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0u);   // the leader's MMA thread owns the accumulators
         else mbar_arrive(&tempty_bar[as]);
@@ -573,14 +677,6 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
   p.kblocks = (a.K + kBlockK - 1) / kBlockK;
   p.err = device_error_word(device);
-  {
-    static int v = -1;
-    if (v < 0) {
-      const char* e = getenv("AGB_EPI_STREAM");
-      v = (e && e[0] == '1') ? 1 : 0;   // measured: -1.0 % step time with the stream hint (each residual row of an upsampling
-    }                                   // epilogue is read twice, and L1 served the second read) -> off by default
-    p.stream_res = v;
-  }
 
   {
     const bool a_shared = a.batch > 1 && a.a_bstride == 0;   // one A for every batch (e.g. a weight as the row operand)
@@ -645,8 +741,29 @@ int launch_gemm(const AgGemmArgs& a, int device, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+#ifdef AGB_TRACE
+  const char* trace_path = getenv("AGB_GEMM_TRACE");
+  if (trace_path) {
+    cudaMalloc(&p.trace, 3 * 2048 * sizeof(unsigned long long));
+    cudaMemsetAsync(p.trace, 0, 3 * 2048 * sizeof(unsigned long long), stream);
+  }
+#endif
   cudaError_t le = cudaLaunchKernelEx(&cfg, fn, p);
   if (le != cudaSuccess) return set_error("ag_gemm_fwd: launch failed: %s", cudaGetErrorString(le));
+#ifdef AGB_TRACE
+  if (trace_path) {
+    static unsigned long long host[3 * 2048];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    if (FILE* f = fopen(trace_path, "w")) {   // the last launch wins
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < 2048 && host[r * 2048 + i]; ++i)
+          fprintf(f, "%d %llx %llu\n", r, host[r * 2048 + i] >> 48, host[r * 2048 + i] & 0xFFFFFFFFFFFFull);
+      fclose(f);
+    }
+  }
+#endif
   return check_launch("ag_gemm_fwd");
 }
 

@@ -20,25 +20,30 @@ bias = torch.randn(C, **f32)
 
 
 ONCE = os.environ.get("PROBE_ONCE") == "1"   # one launch per case (for an ncu --set full capture)
+CASES = [c for c in os.environ.get("PROBE_CASES", "").split(",") if c]   # subset of case names (default: all)
 
 
 def timeit(fn, name, flops):
+    if CASES and name not in CASES:
+        return
     if ONCE:
         fn()
         torch.cuda.synchronize()
         print(f"{name}: launched once", flush=True)
         return
-    for _ in range(2):
+    for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    print(f"{name}: {ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
+    best = 1e9
+    for _ in range(4):            # min over 4 repeats of 8 launches: the first repeats also absorb the clock ramp
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(8):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 8)
+    print(f"{name}: {best:.3f} ms  {flops / best / 1e9:.0f} TFLOP/s", flush=True)
 
 
 # (1) embed: K=64 -> out f32 + actA bf16
