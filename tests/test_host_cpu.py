@@ -43,6 +43,14 @@ def test_struct_layout_matches_header(lib, tmp_path):
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(_lib.AgEpiOut), C.sizeof(_lib.AgGemmArgs), C.sizeof(_lib.AgAttnArgs)]
+    # field offsets too (equal sizes do not rule out two swapped fields): every field of the two argument structs
+    checks = [("AgGemmArgs", _lib.AgGemmArgs), ("AgAttnArgs", _lib.AgAttnArgs)]
+    body = "".join(f'printf("%zu ", offsetof({cn}, {fn}));' for cn, cls in checks for fn, _ in cls._fields_)
+    src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "agb200.h"\nint main(){{{body}return 0;}}\n')
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    offs = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [getattr(cls, fn).offset for _, cls in checks for fn, _ in cls._fields_]
+    assert offs == want
 
 
 def test_no_gpu_is_a_loud_error(lib):

@@ -14,8 +14,9 @@ cap() {  # name, kernel regex, launch-skip
   # the reports are ~30 MB each (imported sources): digest them here, only the CSV / hot-line text travels back
   python tools/ncu_digest.py $O/ncu_r03_$1.ncu-rep $O/ncu_r03_$1 && rm -f $O/ncu_r03_$1.ncu-rep
 }
-# gemm launches: forward 1 issues 119 + 5 (relative-position encodings, cached afterwards), forwards 2 and 3 issue 119:
-# forward 3 starts at 243; inside a forward 114 = ups[6].unet_conv (w1, 1 bp), 118 = outembed_1bp, 0 = the K = 64 embed GEMM
+# gemm launches: forward 1 issues 119 + the cached relative-position encodings, forwards 2 and 3 issue 119; the skips below
+# are approximate — name a capture after the kernel / duration / DRAM bytes it actually holds (the run that produced
+# profiles/ncu_r03_* caught outembed_1bp and the K = 64 embed GEMM as intended and a width-5 conv_out at 2 bp for 357)
 cap outembed_1bp gemm_conv 361
 cap w1conv_768_1bp gemm_conv 357
 cap embed_k64 gemm_conv 243

@@ -1,6 +1,6 @@
 """SASS opcode histogram per kernel of libagb200.so (what proves tcgen05 / TMEM / TMA in the shipped binary):
 
-    python tools/sass_histogram.py > profiles/sass_r02_histogram.md
+    python tools/sass_histogram.py > profiles/sass_r03_histogram.md
 """
 import collections
 import re
@@ -34,7 +34,7 @@ def main():
     demangle = subprocess.run(["c++filt"], input="\n".join(funcs), capture_output=True, text=True).stdout.splitlines()
     print(f"# SASS opcode histogram of alphagenome_b200/libagb200.so ({len(funcs)} functions, arch {sorted(arch)})\n")
     print("Counts of instructions whose mnemonic starts with the column's prefix (`cuobjdump -sass`).  `UTCHMMA` = tcgen05.mma, "
-          "`LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = TMA tile load, `UTCBAR` = tcgen05.commit, `HMMA` would be the legacy mma.sync path (absent).\n")
+          "`LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = TMA tile load, `UTCBAR` = tcgen05.commit, `HMMA` = the legacy warp MMA (`mma.sync`): used by `pair_bias_mma_kernel` only (a 128 -> 8 projection, DESIGN.md section 4), absent from every GEMM / attention kernel.\n")
     print("| kernel | instrs | " + " | ".join(KEY) + " |")
     print("|---|---:|" + "---:|" * len(KEY))
     total = collections.Counter()
