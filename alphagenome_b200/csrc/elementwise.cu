@@ -828,6 +828,8 @@ int launch_pair_bias(const float* pair, const float* scale, const float* shift, 
   if (C != 128) return set_error("ag_pair_bias_fwd: built for pair dim 128 (got %d)", C);
   if (sets != 1 && sets != 2) return set_error("ag_pair_bias_fwd: sets must be 1 or 2 (got %d)", sets);
   if (!pair || !scale || !shift || !W || !bias) return set_error("ag_pair_bias_fwd: null pointer");
+  if ((reinterpret_cast<uintptr_t>(pair) | reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(W)) & 15)
+    return set_error("ag_pair_bias_fwd: pair, scale, shift and W must be 16-byte aligned");
   const long per_b = (long)rows * cols;
   const long cells = (long)B * per_b;
   // tensor-core path: groups of 16 consecutive cells inside one batch element (AGB_PAIR_BIAS_MMA=0: the fp32 FMA kernels)
@@ -836,7 +838,7 @@ int launch_pair_bias(const float* pair, const float* scale, const float* shift, 
     const char* e = getenv("AGB_PAIR_BIAS_MMA");
     use_mma = (e && e[0] == '0') ? 0 : 1;
   }
-  if (use_mma && heads == 8 && per_b % 16 == 0 && (reinterpret_cast<uintptr_t>(pair) & 15) == 0) {
+  if (use_mma && heads == 8 && per_b % 16 == 0) {
     const long groups16 = cells / 16;
     const unsigned grid = grid_for(groups16 * 32, 256, device, 2);
     if (sets == 2) pair_bias_mma_kernel<2><<<grid, 256, 0, st>>>(pair, scale, shift, W, bias, groups16, per_b, set_stride);

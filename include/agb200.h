@@ -162,6 +162,9 @@ typedef struct AgAttnArgs {
   void* norm_out;        /* bf16 or NULL */
 } AgAttnArgs;
 
+/* mode 1 with norm_out (the trunk's call) runs a persistent single-pass kernel: online softmax with a running row maximum
+ * and a lazy rescale of the accumulator — the exact softmax, any n_k; without norm_out the two-pass kernel (n_k <= 512
+ * keys stay resident between its passes, more are re-streamed). */
 int ag_attention_fwd(const AgAttnArgs* args, int device, void* stream);
 
 /* --- vectorised HBM-bound kernels ------------------------------------------------------------------- */
@@ -187,7 +190,9 @@ int ag_transpose_bf16(const void* in, void* out, int32_t nb, int32_t R, int32_t 
 /* to_attn_bias (AG:688-693) of `sets` (1 or 2) attention layers that read the same pair tensor, in one pass over it:
  * bias[s][b][g][i][j] = sum_c W[s][g][c] * gelu_erf(pair[b][i][j][c]*scale[s][c] + shift[s][c]);
  * pair is [B][rows][cols][C] (rows < cols for a sequence-parallel row shard); scale/shift [sets][C]; W [sets][heads][C];
- * bias holds `sets` tensors [B][heads][rows][cols] that are `set_stride` floats apart */
+ * bias holds `sets` tensors [B][heads][rows][cols] that are `set_stride` floats apart.  When rows*cols is a multiple of 16
+ * the projection runs on the tensor core with bf16 operands (like every other contraction of the path); other shapes
+ * take fp32 FMA kernels.  pair, scale, shift and W must be 16-byte aligned. */
 int ag_pair_bias_fwd(const float* pair, const float* scale, const float* shift, const float* W, float* bias,
                      int32_t B, int32_t rows, int32_t cols, int32_t C, int32_t heads, int32_t sets, int64_t set_stride,
                      int device, void* stream);
@@ -305,8 +310,10 @@ int ag_watchdog_status(int device, uint32_t out[4]);
  *     0 = automatic (CTA pairs whenever the problem has at least two 128-row tiles), 1, 2.  Results are bit-identical
  *     either way (same products, same fp32 accumulation order); returns the previous setting.
  *   - environment variables read ONCE per process: AGB_GEMM_CG (seeds the default above), AGB_GEMM_UNIFORM=1 (divisor
- *     N tiling instead of 256-wide tiles + remainder), AGB_ATTN_POLY (exponentials per 8 on the FMA pipe),
- *     AGB_ATTN_SPLIT (force the attention key split off / on), AGB_PDL=0 (no programmatic dependent launch). */
+ *     N tiling instead of 256-wide tiles + remainder), AGB_GEMM_EW=16 (16- instead of 32-column epilogue chunks),
+ *     AGB_ATTN_POLY (exponentials per 8 on the FMA pipe), AGB_ATTN_SPLIT (force the attention key split off / on),
+ *     AGB_ROWATTN=0 (mode-1 attention always on the one-tile-per-CTA two-pass kernel), AGB_PAIR_BIAS_MMA=0 (fp32 FMA
+ *     kernels for ag_pair_bias_fwd), AGB_PDL=0 (no programmatic dependent launch). */
 int ag_gemm_set_cta_group(int cta_group);
 
 #ifdef __cplusplus
