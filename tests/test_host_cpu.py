@@ -230,3 +230,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     r2 = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
                         env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=120)
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_one_mufu_erf_gelu_coefficients():
+    """ag_pair_bias_fwd's tensor-core path evaluates erf-GELU as 0.5 x (1 + tanh(x (c1 + c3 x^2 + c5 x^4))) with x^2 clamped to
+    64 (elementwise.cu: gelu_erf_tanh).  The coefficients are read from the source, so the documented bound (max |error|
+    2.5e-5 against nn.GELU before tanh.approx's own 2^-11) cannot drift from the code."""
+    import math
+    import re
+
+    src = (ROOT / "alphagenome_b200" / "csrc" / "elementwise.cu").read_text()
+    body = src[src.index("float gelu_erf_tanh(float x)"):]
+    body = body[: body.index("}")]
+    c5, c3 = (float(v) for v in re.search(r"fmaf\(t, (-?[\d.e+-]+)f, ([\d.e+-]+)f\)", body).groups())
+    c1 = float(re.search(r"fmaf\(t, q, ([\d.e+-]+)f\)", body).group(1))
+    clamp = float(re.search(r"fminf\(x \* x, ([\d.]+)f\)", body).group(1))
+    x = torch.linspace(-30, 30, 600001, dtype=torch.float64)
+    t = (x * x).clamp(max=clamp)
+    approx = 0.5 * x * (1 + torch.tanh(x * (c1 + t * (c3 + t * c5))))
+    exact = 0.5 * x * (1 + torch.erf(x / math.sqrt(2)))
+    assert (approx - exact).abs().max().item() < 2.6e-5
