@@ -76,13 +76,16 @@ def _build_variant(tag: str, flags: list[str]) -> Path:
     out = PKG / f"libagb200_{tag}.so"
     odir = OBJ_DIR / tag
     odir.mkdir(parents=True, exist_ok=True)
-    objs = []
-    for src in sources():
+    def compile_one(src: Path) -> Path:
         obj = odir / (src.stem + ".o")
         r = subprocess.run([NVCC, *ARCH_FLAGS, *COMMON, *flags, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
-        objs.append(obj)
+        return obj
+
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(compile_one, srcs))
     r = subprocess.run([NVCC, *ARCH_FLAGS, "-shared", "-o", str(out), *map(str, objs), "-Xlinker", "--exclude-libs,ALL"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
