@@ -281,3 +281,49 @@ def test_bench_clock_sampler_keeps_rows_of_the_timed_window(tmp_path, monkeypatc
     out = s.stop()
     assert out["samples"] >= 5 and out["sm_mhz"] == 1500.0 and out["sm_max_mhz"] == 1965.0
     assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_lazy_rescale_online_softmax_is_the_exact_softmax():
+    """The arithmetic of row_attention_kernel (attention.cu), restated in fp64: key blocks of 128, a running row maximum
+    that is only raised — and O / the row sum only rescaled — when a block's maximum exceeds it by more than 2^8, weights
+    taken relative to the (possibly stale) running maximum.  Whatever the stale maximum is, it scales P and the row sum
+    alike, so the quotient is the exact softmax; and no weight ever exceeds 2^8."""
+    import math
+
+    g = torch.Generator().manual_seed(0)
+    n_q, n_k, d, dv, blk = 64, 640, 128, 128, 128
+    q = torch.randn(n_q, d, generator=g, dtype=torch.float64) * 1.5
+    k = torch.randn(n_k, d, generator=g, dtype=torch.float64) * 1.5
+    k[128:] *= 4.0                      # later blocks raise most row maxima by far more than the threshold ...
+    k[256:384] *= 0.02                  # ... one block does not ...
+    q[::5] *= 0.01                      # ... and some rows never cross it (stale maximum kept for the whole row)
+    v = torch.randn(n_k, dv, generator=g, dtype=torch.float64)
+    scale = d ** -0.5
+    c = scale * math.log2(math.e)       # the kernel works in the log2 domain: p = 2^(s c - m c)
+    s = q @ k.T
+    want = torch.softmax(s * scale, dim=-1) @ v
+
+    m_run = torch.zeros(n_q, dtype=torch.float64)
+    rsum = torch.zeros(n_q, dtype=torch.float64)
+    O = torch.zeros(n_q, dv, dtype=torch.float64)
+    rescales, pmax = 0, 0.0
+    for j in range(0, n_k, blk):
+        sb = s[:, j:j + blk]
+        bmax = sb.max(dim=1).values
+        if j == 0:
+            m_run = bmax.clone()
+        else:
+            grow = (bmax - m_run) * c > 8.0
+            fac = torch.where(grow, torch.exp2((m_run - bmax) * c), torch.ones_like(m_run))
+            m_run = torch.where(grow, bmax, m_run)
+            rsum *= fac
+            O *= fac[:, None]
+            rescales += int(grow.sum())
+        p = torch.exp2((sb - m_run[:, None]) * c)
+        pmax = max(pmax, float(p.max()))
+        rsum += p.sum(dim=1)
+        O += p @ v[j:j + blk]
+    got = O / rsum[:, None]
+    assert rescales > 0 and rescales < n_q * (n_k // blk - 1), "the case must mix rescaled and non-rescaled (row, block) pairs"
+    assert pmax <= 2.0 ** 8 * (1 + 1e-12)
+    assert (got - want).abs().max().item() < 1e-12
